@@ -1,0 +1,605 @@
+// C ABI of libqgb200 (include/qgb200.h): handle life cycle, spectral plan, host <-> device
+// state transfer in the reference's array layout, the step loop, diagnostics.
+#include <cudaTypedefs.h>
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <mutex>
+#include <new>
+
+#include "qg_internal.cuh"
+
+namespace qg {
+
+static thread_local std::string g_create_error = "";
+
+static int fail(Handle* h, int code, const std::string& msg) {
+    if (h) h->err = msg; else g_create_error = msg;
+    return code;
+}
+
+#define QG_CUDA(h, expr)                                                                   \
+    do {                                                                                   \
+        cudaError_t _e = (expr);                                                           \
+        if (_e != cudaSuccess) {                                                           \
+            char _b[512];                                                                  \
+            snprintf(_b, sizeof(_b), "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), \
+                     __FILE__, __LINE__);                                                  \
+            return fail(h, _e == cudaErrorMemoryAllocation ? QG_ERR_NOMEM : QG_ERR_CUDA, _b); \
+        }                                                                                  \
+    } while (0)
+
+// ------------------------------------------------------------------------------------------
+// host <-> device layout conversion
+// ------------------------------------------------------------------------------------------
+// host array: (M+2, P+2, 2, 3) column-major per member, level 0 newest.
+__global__ void k_unpack(const double* __restrict__ host, double* __restrict__ dev, Geom g, int nm,
+                         int slot0, int s1, int s2) {
+    // one thread per padded device cell (ghost width 2) of one (level, member, layer) field
+    const int ix = blockIdx.x * blockDim.x + threadIdx.x - GHOST;   // -2 .. M+1
+    const int iy = blockIdx.y - GHOST;                              // -2 .. P+1
+    if (ix >= g.M + GHOST) return;
+    int z = blockIdx.z;   // (level * nm + member) * 2 + layer
+    const int layer = z & 1;
+    z >>= 1;
+    const int member = z % nm, level = z / nm;
+    const int slot = level == 0 ? slot0 : (level == 1 ? s1 : s2);
+    const int i = ((ix % g.M) + g.M) % g.M, j = ((iy % g.P) + g.P) % g.P;
+    const int64_t hs = (int64_t)(g.M + 2) * (g.P + 2);
+    const double v = host[(int64_t)member * 6 * hs + (int64_t)(level * 2 + layer) * hs +
+                          (int64_t)(j + 1) * (g.M + 2) + (i + 1)];
+    dev[((int64_t)(slot * nm + member) * 2 + layer) * g.fstride + g.at(ix, iy)] = v;
+}
+
+__global__ void k_pack(const double* __restrict__ dev, double* __restrict__ host, Geom g, int nm,
+                       int slot0, int s1, int s2, const double* __restrict__ shift, double sh0,
+                       double sh1) {
+    const int ih = blockIdx.x * blockDim.x + threadIdx.x;   // 0 .. M+1 (host index incl. ghost)
+    const int jh = blockIdx.y;                              // 0 .. P+1
+    if (ih >= g.M + 2) return;
+    int z = blockIdx.z;
+    const int layer = z & 1;
+    z >>= 1;
+    const int member = z % nm, level = z / nm;
+    const int slot = level == 0 ? slot0 : (level == 1 ? s1 : s2);
+    const int i = ((ih - 1) % g.M + g.M) % g.M, j = ((jh - 1) % g.P + g.P) % g.P;
+    const int64_t hs = (int64_t)(g.M + 2) * (g.P + 2);
+    double v = dev[((int64_t)(slot * nm + member) * 2 + layer) * g.fstride + g.at(i, j)];
+    (void)shift; (void)sh0; (void)sh1;
+    host[(int64_t)member * 6 * hs + (int64_t)(level * 2 + layer) * hs + (int64_t)jh * (g.M + 2) + ih] = v;
+}
+
+// ------------------------------------------------------------------------------------------
+// diagnostics (DESIGN.md "Diagnostics")
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k5_diag_partial(const double* __restrict__ q, const double* __restrict__ psi, Geom g, double hdx,
+                double H1, double H2, double S1, double* __restrict__ part) {
+    __shared__ double sh[32];
+    const int member = blockIdx.y;
+    const double* __restrict__ q1 = q + (int64_t)member * 2 * g.fstride;
+    const double* __restrict__ q2 = q1 + g.fstride;
+    const double* __restrict__ p1 = psi + (int64_t)member * 2 * g.fstride;
+    const double* __restrict__ p2 = p1 + g.fstride;
+    double e = 0.0, zz = 0.0;
+    for (int j = blockIdx.x; j < g.P; j += gridDim.x) {
+        for (int i = threadIdx.x; i < g.M; i += blockDim.x) {
+            const int64_t o = g.at(i, j);
+            const double ux1 = hdx * (p1[o + 1] - p1[o - 1]), uy1 = hdx * (p1[o + g.pitch] - p1[o - g.pitch]);
+            const double ux2 = hdx * (p2[o + 1] - p2[o - 1]), uy2 = hdx * (p2[o + g.pitch] - p2[o - g.pitch]);
+            const double dp = p1[o] - p2[o];
+            e += H1 * (ux1 * ux1 + uy1 * uy1) + H2 * (ux2 * ux2 + uy2 * uy2) + H1 * S1 * dp * dp;
+            zz += H1 * q1[o] * q1[o] + H2 * q2[o] * q2[o];
+        }
+    }
+    const double et = block_sum(e, sh);
+    const double zt = block_sum(zz, sh);
+    if (threadIdx.x == 0) {
+        part[((int64_t)member * gridDim.x + blockIdx.x) * 2 + 0] = et;
+        part[((int64_t)member * gridDim.x + blockIdx.x) * 2 + 1] = zt;
+    }
+}
+
+__global__ void __launch_bounds__(256)
+k5_diag_final(const double* __restrict__ part, int nb, double scale, double* __restrict__ out) {
+    __shared__ double sh[32];
+    const int member = blockIdx.x;
+    double e = 0.0, zz = 0.0;
+    for (int b = threadIdx.x; b < nb; b += blockDim.x) {
+        e += part[((int64_t)member * nb + b) * 2 + 0];
+        zz += part[((int64_t)member * nb + b) * 2 + 1];
+    }
+    const double et = block_sum(e, sh);
+    const double zt = block_sum(zz, sh);
+    if (threadIdx.x == 0) {
+        out[member * 2 + 0] = scale * et;
+        out[member * 2 + 1] = scale * zt;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// spectral plan
+// ------------------------------------------------------------------------------------------
+static int ilog2_exact(int n) {
+    int l = 0;
+    while ((1 << l) < n) ++l;
+    return (1 << l) == n ? l : -1;
+}
+
+static void exact_twiddle(int n, int N, long double* c, long double* s) {
+    // exp(-2 pi i n / N) evaluated in 80-bit extended precision (argument error ~3e-19, far
+    // below half a double ulp); multiples of a quarter turn are forced to their exact values.
+    const long double PI = 3.14159265358979323846264338327950288L;
+    if (n == 0) { *c = 1.0L; *s = 0.0L; return; }
+    if (4LL * n == N) { *c = 0.0L; *s = -1.0L; return; }
+    if (2LL * n == N) { *c = -1.0L; *s = 0.0L; return; }
+    if (4LL * n == 3LL * N) { *c = 0.0L; *s = 1.0L; return; }
+    const long double th = 2.0L * PI * (long double)n / (long double)N;
+    *c = cosl(th);
+    *s = -sinl(th);
+}
+
+template <typename T>
+static cudaError_t upload_vec(T** dptr, const std::vector<T>& v) {
+    cudaError_t e = cudaMalloc((void**)dptr, v.size() * sizeof(T));
+    if (e != cudaSuccess) return e;
+    return cudaMemcpy(*dptr, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice);
+}
+
+cudaError_t build_plan(Handle* h) {
+    Plan& pl = h->plan;
+    memset(&pl, 0, sizeof(pl));
+    const int M = h->g.M, P = h->g.P;
+    pl.M = M;
+    pl.P = P;
+    pl.ncol = 2 * M;
+    pl.log2M = ilog2_exact(M);
+    pl.pow2 = (pl.log2M >= 3 && M <= 8192) ? 1 : 0;
+    if (pl.pow2) {
+        pl.tpr = M / 8;
+        pl.rpb = pl.tpr >= 128 ? 1 : 128 / pl.tpr;
+    }
+    pl.C = (P + 31) / 32;
+    pl.lenLast = P - 32 * (pl.C - 1);
+    pl.wpc = pl.C < 16 ? pl.C : 16;
+    {
+        int need = (pl.C + pl.wpc - 1) / pl.wpc;
+        int cs = 1;
+        while (cs < need && cs < 8) cs *= 2;
+        pl.CS = cs;
+        pl.m = (pl.C + cs * pl.wpc - 1) / (cs * pl.wpc);
+    }
+    pl.k0scale = h->prm.dx * h->prm.dx / M;
+
+    std::vector<double2> tw(M);
+    for (int n = 0; n < M; ++n) {
+        long double c, s;
+        exact_twiddle(n, M, &c, &s);
+        tw[n] = make_double2((double)c, (double)s);
+    }
+    const long double PI = 3.14159265358979323846264338327950288L;
+    const long double dx2 = (long double)h->prm.dx * (long double)h->prm.dx;
+    std::vector<double> rtab(pl.ncol), kap(pl.ncol), rho32(pl.ncol), h32(pl.ncol), rhoL(pl.ncol),
+        hL(pl.ncol), inv1(pl.ncol), pinw(pl.ncol);
+    for (int col = 0; col < pl.ncol; ++col) {
+        const int s = col >> 1, part = col & 1;
+        int field, k;
+        if (s == 0) { field = part; k = 0; }
+        else if ((M % 2 == 0) && s == M / 2) { field = part; k = M / 2; }
+        else if (2 * s < M) { field = 0; k = s; }
+        else { field = 1; k = M - s; }
+        const long double sn = sinl(PI * k / M);
+        long double e = 4.0L * sn * sn;
+        if (field == 1) e -= (long double)h->prm.alpha * dx2;
+        long double r = 0.0L;
+        const bool singular = !(e > 0.0L);
+        if (!singular) r = 2.0L / ((2.0L + e) + sqrtl(e * (e + 4.0L)));
+        const long double r32 = powl(r, 32), rL = powl(r, pl.lenLast), rP = powl(r, P);
+        const long double geo32 = singular ? 0.0L : r * (1.0L - r32 * r32) / (1.0L - r * r);
+        const long double geoL = singular ? 0.0L : r * (1.0L - rL * rL) / (1.0L - r * r);
+        rtab[col] = (double)r;
+        kap[col] = singular ? 0.0 : (double)(-r * dx2 / M);
+        rho32[col] = (double)r32;
+        rhoL[col] = (double)rL;
+        h32[col] = (double)geo32;
+        hL[col] = (double)geoL;
+        inv1[col] = singular ? 1.0 : (double)(1.0L / (1.0L - rP));
+        const bool is_re = (s == 0 || ((M % 2 == 0) && s == M / 2)) ? true : (part == 0);
+        pinw[col] = (field == 0 && is_re) ? 1.0 : 0.0;
+    }
+    cudaError_t e;
+    if ((e = upload_vec(&pl.tw, tw)) != cudaSuccess) return e;
+    if ((e = upload_vec(&pl.rtab, rtab)) != cudaSuccess) return e;
+    if ((e = upload_vec(&pl.kap, kap)) != cudaSuccess) return e;
+    if ((e = upload_vec(&pl.rho32, rho32)) != cudaSuccess) return e;
+    if ((e = upload_vec(&pl.h32, h32)) != cudaSuccess) return e;
+    if ((e = upload_vec(&pl.rhoL, rhoL)) != cudaSuccess) return e;
+    if ((e = upload_vec(&pl.hL, hL)) != cudaSuccess) return e;
+    if ((e = upload_vec(&pl.inv1mrP, inv1)) != cudaSuccess) return e;
+    if ((e = upload_vec(&pl.pinw, pinw)) != cudaSuccess) return e;
+    h->plan_ok = true;
+    return cudaSuccess;
+}
+
+void free_plan(Handle* h) {
+    Plan& pl = h->plan;
+    cudaFree(pl.tw); cudaFree(pl.rtab); cudaFree(pl.kap); cudaFree(pl.rho32); cudaFree(pl.h32);
+    cudaFree(pl.rhoL); cudaFree(pl.hL); cudaFree(pl.inv1mrP); cudaFree(pl.pinw);
+    memset(&pl, 0, sizeof(pl));
+    h->plan_ok = false;
+}
+
+static int make_tensor_map(Handle* h, CUtensorMap* tm, double* base) {
+    static PFN_cuTensorMapEncodeTiled_v12000 encode = nullptr;
+    if (!encode) {
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+        if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || !fn)
+            return fail(h, QG_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+        encode = (PFN_cuTensorMapEncodeTiled_v12000)fn;
+    }
+    const cuuint64_t dims[3] = {(cuuint64_t)h->g.pitch, (cuuint64_t)h->g.rows, (cuuint64_t)h->nfields};
+    const cuuint64_t strides[2] = {(cuuint64_t)h->g.pitch * sizeof(double),
+                                   (cuuint64_t)h->g.fstride * sizeof(double)};
+    const cuuint32_t box[3] = {K1_BX, K1_BY, 1};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = encode(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, base, dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                        CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        char b[128];
+        snprintf(b, sizeof(b), "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+        return fail(h, QG_ERR_CUDA, b);
+    }
+    return QG_OK;
+}
+
+cudaError_t launch_diag(Handle* h) {
+    const int nb = h->diag_blocks;
+    const double inv = 1.0 / h->prm.dx;
+    {
+        KernelTimer t(h, QG_K_DIAG);
+        k5_diag_partial<<<dim3(nb, h->nm), 256, 0, h->stream>>>(
+            h->field(h->q, h->qcur, 0, 0), h->field(h->psi, h->pcur, 0, 0), h->g, 0.5 * inv, h->prm.H1,
+            h->prm.H2, h->prm.S1, h->diag_part);
+    }
+    {
+        KernelTimer t(h, QG_K_DIAG);
+        k5_diag_final<<<h->nm, 256, 0, h->stream>>>(h->diag_part, nb, 0.5 * h->prm.dx * h->prm.dx,
+                                                   h->diag_part + (int64_t)h->nm * nb * 2);
+    }
+    return cudaGetLastError();
+}
+
+static int do_evolve_psi(Handle* h) {
+    const int nxt = (h->pcur + 1) % 3;
+    QG_CUDA(h, launch_fft_forward(h, h->field(h->q, h->qcur, 0, 0), 0));
+    QG_CUDA(h, launch_ysolve(h, 1, 0));
+    QG_CUDA(h, launch_fft_inverse(h, h->field(h->psi, nxt, 0, 0), 1));
+    h->pcur = nxt;
+    return QG_OK;
+}
+
+}  // namespace qg
+
+using namespace qg;
+
+extern "C" {
+
+int qg_abi_version(void) { return QG_ABI_VERSION; }
+
+const char* qg_last_error(const qg_handle* h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+const char* qg_kernel_name(int id) {
+    static const char* names[QG_NKERNELS] = {"k1_zeta_step", "k2_fft_forward", "k3_pre", "k3_ysolve",
+                                             "k3_gauge", "k4_fft_inverse", "k5_diag", "k_pack"};
+    return (id >= 0 && id < QG_NKERNELS) ? names[id] : "?";
+}
+
+int qg_create(const qg_params* p, int device, int nmembers, void* stream, qg_handle** out) {
+    if (!p || !out) return fail(nullptr, QG_ERR_INVALID, "qg_create: null argument");
+    *out = nullptr;
+    if (p->M < 3 || p->P < 3) return fail(nullptr, QG_ERR_INVALID, "qg_create: M and P must be >= 3");
+    if (nmembers < 1 || nmembers > 16384) return fail(nullptr, QG_ERR_INVALID, "qg_create: bad nmembers");
+    if (!(p->dx > 0.0)) return fail(nullptr, QG_ERR_INVALID, "qg_create: dx must be positive");
+    if (!(p->alpha < 0.0))
+        return fail(nullptr, QG_ERR_INVALID, "qg_create: alpha (S_eig) must be negative (modified Helmholtz)");
+    if (p->P > 16384) return fail(nullptr, QG_ERR_INVALID, "qg_create: P > 16384 not supported");
+    const bool pow2 = (p->M & (p->M - 1)) == 0 && p->M >= 8;
+    if (pow2 && p->M > 8192) return fail(nullptr, QG_ERR_INVALID, "qg_create: M > 8192 not supported yet");
+    if (!pow2 && p->M > 4096)
+        return fail(nullptr, QG_ERR_INVALID, "qg_create: non-power-of-two M > 4096 not supported");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0 || device < 0 || device >= ndev) {
+        cudaGetLastError();
+        return fail(nullptr, QG_ERR_NODEVICE, "qg_create: no CUDA device (there is no CPU fallback)");
+    }
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess || prop.major < 10)
+        return fail(nullptr, QG_ERR_NODEVICE, "qg_create: device is not sm_100 class (there is no CPU fallback)");
+    if (cudaSetDevice(device) != cudaSuccess) return fail(nullptr, QG_ERR_CUDA, "cudaSetDevice failed");
+
+    qg_handle* h = new (std::nothrow) qg_handle();
+    if (!h) return fail(nullptr, QG_ERR_NOMEM, "qg_create: out of host memory");
+    h->prm = *p;
+    h->device = device;
+    h->nm = nmembers;
+    h->g.M = p->M;
+    h->g.P = p->P;
+    h->g.pitch = ((XPAD + p->M + GHOST + 15) / 16) * 16;
+    h->g.rows = p->P + 2 * YPAD;
+    h->g.fstride = (int64_t)h->g.pitch * h->g.rows;
+    h->nfields = 3 * nmembers * 2;
+    int rc = QG_OK;
+    auto bail = [&](int code) { std::string m = h->err; qg_destroy(h); g_create_error = m; return code; };
+#define QG_TRY(expr)                                                        \
+    do {                                                                    \
+        cudaError_t _e = (expr);                                            \
+        if (_e != cudaSuccess) {                                            \
+            h->err = std::string(#expr) + ": " + cudaGetErrorString(_e);    \
+            return bail(_e == cudaErrorMemoryAllocation ? QG_ERR_NOMEM : QG_ERR_CUDA); \
+        }                                                                   \
+    } while (0)
+    if (stream) {
+        h->stream = (cudaStream_t)stream;
+    } else {
+        QG_TRY(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+        h->own_stream = true;
+    }
+    QG_TRY(cudaEventCreate(&h->ev0));
+    QG_TRY(cudaEventCreate(&h->ev1));
+    const size_t fbytes = (size_t)h->nfields * h->g.fstride * sizeof(double);
+    QG_TRY(cudaMalloc((void**)&h->q, fbytes));
+    QG_TRY(cudaMalloc((void**)&h->psi, fbytes));
+    QG_TRY(cudaMalloc((void**)&h->f, fbytes));
+    QG_TRY(cudaMemsetAsync(h->q, 0, fbytes, h->stream));
+    QG_TRY(cudaMemsetAsync(h->psi, 0, fbytes, h->stream));
+    QG_TRY(cudaMemsetAsync(h->f, 0, fbytes, h->stream));
+    QG_TRY(cudaMalloc((void**)&h->S, (size_t)nmembers * p->P * 2 * p->M * sizeof(double)));
+    QG_TRY(cudaMalloc((void**)&h->k0sol, (size_t)nmembers * p->P * sizeof(double)));
+    QG_TRY(cudaMalloc((void**)&h->scal, (size_t)nmembers * 4 * sizeof(double)));
+    QG_TRY(cudaMemsetAsync(h->scal, 0, (size_t)nmembers * 4 * sizeof(double), h->stream));
+    h->diag_blocks = p->P < 592 ? p->P : 592;
+    QG_TRY(cudaMalloc((void**)&h->diag_part, ((size_t)nmembers * h->diag_blocks * 2 + 2 * nmembers) * sizeof(double)));
+    QG_TRY(build_plan(h));
+    rc = make_tensor_map(h, &h->tm_q, h->q);
+    if (rc == QG_OK) rc = make_tensor_map(h, &h->tm_psi, h->psi);
+    if (rc != QG_OK) return bail(rc);
+    QG_TRY(cudaStreamSynchronize(h->stream));
+#undef QG_TRY
+    *out = h;
+    return QG_OK;
+}
+
+int qg_destroy(qg_handle* h) {
+    if (!h) return QG_OK;
+    cudaSetDevice(h->device);
+    if (h->stream) cudaStreamSynchronize(h->stream);
+    free_plan(h);
+    cudaFree(h->q); cudaFree(h->psi); cudaFree(h->f); cudaFree(h->S); cudaFree(h->k0sol);
+    cudaFree(h->scal); cudaFree(h->stage); cudaFree(h->diag_part);
+    if (h->ev0) cudaEventDestroy(h->ev0);
+    if (h->ev1) cudaEventDestroy(h->ev1);
+    if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+    return QG_OK;
+}
+
+static int ensure_stage(qg_handle* h) {
+    if (h->stage) return QG_OK;
+    const size_t n = (size_t)h->nm * 6 * (h->g.M + 2) * (h->g.P + 2);
+    QG_CUDA(h, cudaMalloc((void**)&h->stage, n * sizeof(double)));
+    return QG_OK;
+}
+
+static int upload_one(qg_handle* h, const double* host, double* dev, int cur) {
+    const size_t n = (size_t)h->nm * 6 * (h->g.M + 2) * (h->g.P + 2);
+    QG_CUDA(h, cudaMemcpyAsync(h->stage, host, n * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    dim3 block(128), grid((h->g.M + 2 * GHOST + 127) / 128, h->g.P + 2 * GHOST, 3 * h->nm * 2);
+    {
+        KernelTimer t(h, QG_K_PACK);
+        k_unpack<<<grid, block, 0, h->stream>>>(h->stage, dev, h->g, h->nm, cur, (cur + 2) % 3, (cur + 1) % 3);
+    }
+    QG_CUDA(h, cudaGetLastError());
+    return QG_OK;
+}
+
+static int download_one(qg_handle* h, const double* dev, double* host, int cur) {
+    const size_t n = (size_t)h->nm * 6 * (h->g.M + 2) * (h->g.P + 2);
+    dim3 block(128), grid((h->g.M + 2 + 127) / 128, h->g.P + 2, 3 * h->nm * 2);
+    {
+        KernelTimer t(h, QG_K_PACK);
+        k_pack<<<grid, block, 0, h->stream>>>(dev, h->stage, h->g, h->nm, cur, (cur + 2) % 3, (cur + 1) % 3,
+                                              nullptr, 0.0, 0.0);
+    }
+    QG_CUDA(h, cudaGetLastError());
+    QG_CUDA(h, cudaMemcpyAsync(host, h->stage, n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    QG_CUDA(h, cudaStreamSynchronize(h->stream));
+    return QG_OK;
+}
+
+int qg_upload_state(qg_handle* h, const double* zeta, const double* psi, const double* f_store) {
+    if (!h) return QG_ERR_INVALID;
+    QG_CUDA(h, cudaSetDevice(h->device));
+    int rc = ensure_stage(h);
+    if (rc) return rc;
+    if (zeta) {
+        h->qcur = 0;
+        if ((rc = upload_one(h, zeta, h->q, 0))) return rc;
+        if (!f_store && !h->have_state)
+            QG_CUDA(h, cudaMemsetAsync(h->f, 0, (size_t)h->nfields * h->g.fstride * sizeof(double), h->stream));
+    }
+    if (f_store) {
+        // f_store shares the rotation counter of zeta (both are pushed by evolve_zeta!)
+        if ((rc = upload_one(h, f_store, h->f, h->qcur))) return rc;
+    }
+    if (psi) {
+        h->pcur = 0;
+        if ((rc = upload_one(h, psi, h->psi, 0))) return rc;
+    }
+    QG_CUDA(h, cudaStreamSynchronize(h->stream));   // host buffers are borrowed only for the call
+    h->have_state = true;
+    return QG_OK;
+}
+
+int qg_download_state(qg_handle* h, double* zeta, double* psi, double* f_store) {
+    if (!h) return QG_ERR_INVALID;
+    if (!h->have_state) return fail(h, QG_ERR_STATE, "qg_download_state: no state uploaded");
+    QG_CUDA(h, cudaSetDevice(h->device));
+    int rc = ensure_stage(h);
+    if (rc) return rc;
+    if (zeta && (rc = download_one(h, h->q, zeta, h->qcur))) return rc;
+    if (psi && (rc = download_one(h, h->psi, psi, h->pcur))) return rc;
+    if (f_store && (rc = download_one(h, h->f, f_store, h->qcur))) return rc;
+    return QG_OK;
+}
+
+int qg_evolve_zeta(qg_handle* h, int timestep) {
+    if (!h) return QG_ERR_INVALID;
+    if (!h->have_state) return fail(h, QG_ERR_STATE, "qg_evolve_zeta: no state uploaded");
+    if (timestep < 1) return fail(h, QG_ERR_INVALID, "qg_evolve_zeta: timestep is 1-based");
+    QG_CUDA(h, cudaSetDevice(h->device));
+    QG_CUDA(h, launch_zeta(h, timestep));
+    return QG_OK;
+}
+
+int qg_evolve_psi(qg_handle* h) {
+    if (!h) return QG_ERR_INVALID;
+    if (!h->have_state) return fail(h, QG_ERR_STATE, "qg_evolve_psi: no state uploaded");
+    QG_CUDA(h, cudaSetDevice(h->device));
+    return do_evolve_psi(h);
+}
+
+int qg_step(qg_handle* h, int first_timestep, int nsteps) {
+    if (!h) return QG_ERR_INVALID;
+    if (!h->have_state) return fail(h, QG_ERR_STATE, "qg_step: no state uploaded");
+    if (first_timestep < 1 || nsteps < 0) return fail(h, QG_ERR_INVALID, "qg_step: bad timestep range");
+    QG_CUDA(h, cudaSetDevice(h->device));
+    for (int t = first_timestep; t < first_timestep + nsteps; ++t) {
+        QG_CUDA(h, launch_zeta(h, t));
+        int rc = do_evolve_psi(h);
+        if (rc) return rc;
+    }
+    return QG_OK;
+}
+
+int qg_sync(qg_handle* h) {
+    if (!h) return QG_ERR_INVALID;
+    QG_CUDA(h, cudaSetDevice(h->device));
+    QG_CUDA(h, cudaStreamSynchronize(h->stream));
+    QG_CUDA(h, cudaGetLastError());
+    return QG_OK;
+}
+
+int qg_diagnostics(qg_handle* h, double* energy, double* enstrophy) {
+    if (!h || !energy || !enstrophy) return QG_ERR_INVALID;
+    if (!h->have_state) return fail(h, QG_ERR_STATE, "qg_diagnostics: no state uploaded");
+    QG_CUDA(h, cudaSetDevice(h->device));
+    QG_CUDA(h, launch_diag(h));
+    std::vector<double> out(2 * h->nm);
+    QG_CUDA(h, cudaMemcpyAsync(out.data(), h->diag_part + (int64_t)h->nm * h->diag_blocks * 2,
+                               out.size() * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    QG_CUDA(h, cudaStreamSynchronize(h->stream));
+    for (int m = 0; m < h->nm; ++m) {
+        energy[m] = out[2 * m];
+        enstrophy[m] = out[2 * m + 1];
+    }
+    return QG_OK;
+}
+
+int qg_solve(qg_handle* h, int pinned, const double* f, double* u) {
+    if (!h || !f || !u) return QG_ERR_INVALID;
+    QG_CUDA(h, cudaSetDevice(h->device));
+    int rc = ensure_stage(h);
+    if (rc) return rc;
+    // Scratch: slot (qcur+1)%3 of q (the oldest PV level, about to be overwritten by the next
+    // evolve_zeta anyway) would clobber downloadable history, so use the spectral scratch path
+    // on dedicated temporaries instead.
+    const Geom& g = h->g;
+    const size_t hn = (size_t)(g.M + 2) * (g.P + 2);
+    double* tmp = nullptr;   // two padded fields in, two out
+    QG_CUDA(h, cudaMalloc((void**)&tmp, 4 * g.fstride * sizeof(double)));
+    std::vector<double> hostbuf((size_t)h->nm * 6 * hn, 0.0);
+    // level 0, layers 0 and 1 of member 0 both carry f: field 1 solves Poisson, field 2 Helmholtz
+    memcpy(hostbuf.data(), f, hn * sizeof(double));
+    memcpy(hostbuf.data() + hn, f, hn * sizeof(double));
+    cudaError_t e = cudaMemcpyAsync(h->stage, hostbuf.data(), 2 * hn * sizeof(double), cudaMemcpyHostToDevice, h->stream);
+    if (e == cudaSuccess) {
+        dim3 block(128), grid((g.M + 2 * GHOST + 127) / 128, g.P + 2 * GHOST, 2);
+        KernelTimer t(h, QG_K_PACK);
+        k_unpack<<<grid, block, 0, h->stream>>>(h->stage, tmp, g, 1, 0, 0, 0);
+        e = cudaGetLastError();
+    }
+    // identity projections: psi~ = solve(f) per field
+    qg_params saved = h->prm;
+    const double I4[4] = {1.0, 0.0, 0.0, 1.0};
+    memcpy(h->prm.Pinv, I4, sizeof(I4));
+    memcpy(h->prm.Pfwd, I4, sizeof(I4));
+    const int nm_saved = h->nm;
+    h->nm = 1;
+    if (e == cudaSuccess) e = launch_fft_forward(h, tmp, 0);
+    if (e == cudaSuccess) e = launch_ysolve(h, pinned ? 1 : 0, 0);
+    if (e == cudaSuccess) e = launch_fft_inverse(h, tmp + 2 * g.fstride, pinned ? 1 : 0);
+    if (e == cudaSuccess) {
+        dim3 block(128), grid((g.M + 2 + 127) / 128, g.P + 2, 2);
+        KernelTimer t(h, QG_K_PACK);
+        k_pack<<<grid, block, 0, h->stream>>>(tmp + 2 * g.fstride, h->stage, g, 1, 0, 0, 0, nullptr, 0.0, 0.0);
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess)
+        e = cudaMemcpyAsync(u, h->stage + (pinned ? 0 : hn), hn * sizeof(double), cudaMemcpyDeviceToHost, h->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+    h->nm = nm_saved;
+    h->prm = saved;
+    cudaFree(tmp);
+    QG_CUDA(h, e);
+    return QG_OK;
+}
+
+int qg_set_profiling(qg_handle* h, int enabled) {
+    if (!h) return QG_ERR_INVALID;
+    h->profiling = enabled ? 1 : 0;
+    for (int i = 0; i < QG_NKERNELS; ++i) { h->kms[i] = 0.0; h->kcount[i] = 0; }
+    return QG_OK;
+}
+
+int qg_kernel_times(qg_handle* h, double* ms, int64_t* launches) {
+    if (!h) return QG_ERR_INVALID;
+    for (int i = 0; i < QG_NKERNELS; ++i) {
+        if (ms) ms[i] = h->kms[i];
+        if (launches) launches[i] = h->kcount[i];
+    }
+    return QG_OK;
+}
+
+int64_t qg_launch_count(const qg_handle* h) { return h ? h->launches : 0; }
+
+int qg_device_layout(qg_handle* h, int which, void** base, int64_t* pitch, int64_t* xpad, int64_t* ypad,
+                     int64_t* field_stride) {
+    if (!h) return QG_ERR_INVALID;
+    void* b = nullptr;
+    switch (which) {
+        case 0: b = h->q; break;
+        case 1: b = h->psi; break;
+        case 2: b = h->f; break;
+        case 3: b = h->S; break;
+        default: return fail(h, QG_ERR_INVALID, "qg_device_layout: which must be 0..3");
+    }
+    if (base) *base = b;
+    if (which == 3) {
+        if (pitch) *pitch = h->plan.ncol;
+        if (xpad) *xpad = 0;
+        if (ypad) *ypad = 0;
+        if (field_stride) *field_stride = (int64_t)h->plan.P * h->plan.ncol;
+    } else {
+        if (pitch) *pitch = h->g.pitch;
+        if (xpad) *xpad = XPAD;
+        if (ypad) *ypad = YPAD;
+        if (field_stride) *field_stride = h->g.fstride;
+    }
+    return QG_OK;
+}
+
+}  // extern "C"

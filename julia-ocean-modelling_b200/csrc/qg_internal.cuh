@@ -1,0 +1,211 @@
+// Internal declarations shared by the CUDA translation units of libqgb200.
+// Public surface: include/qgb200.h.  Everything here is sm_100a-only.
+#pragma once
+
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string>
+#include <vector>
+
+#include "qgb200.h"
+
+namespace qg {
+
+// ---- device layout of one field ------------------------------------------------------
+// A field is a (P + 2*YPAD) x pitch array of doubles; interior node (i, j) lives at
+// (j + YPAD) * pitch + XPAD + i.  XPAD = 16 doubles keeps interior rows 128-byte aligned;
+// two ghost columns / rows on every side hold the periodic images (the biharmonic term
+// reaches +-2, the reference gets away with one ghost because it refreshes the ghosts of
+// the intermediate Laplacian, src/schemes/laplacian.jl:25).
+constexpr int XPAD = 16;
+constexpr int YPAD = 2;
+constexpr int GHOST = 2;
+
+// K1 tile geometry (k1_zeta.cu); the TMA box is (K1_BX, K1_BY, 1).
+constexpr int K1_TX = 128;
+constexpr int K1_TY = 16;
+constexpr int K1_BX = K1_TX + 2 * GHOST;   // 132 doubles = 1056 B (multiple of 16 B)
+constexpr int K1_BY = K1_TY + 2 * GHOST;   // 20
+
+struct Geom {
+    int M, P;
+    int pitch;        // doubles per row, multiple of 16
+    int rows;         // P + 2*YPAD
+    int64_t fstride;  // doubles per field = pitch * rows
+    __host__ __device__ int64_t at(int i, int j) const {
+        return (int64_t)(j + YPAD) * pitch + XPAD + i;
+    }
+};
+
+// ---- zeta step (K1) -------------------------------------------------------------------
+struct ZetaArgs {
+    Geom g;
+    const double* f1;   // RHS of step n-1, field 0 of this launch (member 0, layer 0)
+    const double* f2;   // RHS of step n-2
+    double* fn;         // RHS of step n (output)
+    double* qn;         // new PV (output)
+    int zq, zpsi;       // first field index (tensor-map z coordinate) of q / psi inputs
+    int euler;          // 1: steps 1-2 (no history read)
+    double idx2;        // (1/dx)^2
+    double hdx;         // 0.5*(1/dx)
+    double i12dx2;      // 1 / (3*4*dx^2)
+    double visc, dt;
+    double beta[2];     // beta_1, beta_2
+    double U, r;
+    double c1, c2, c3;  // 23/12, 16/12, 5/12
+};
+
+// ---- spectral plan ------------------------------------------------------------------
+// Spectral rows hold both modal fields as M complex slots (2M real columns):
+// slot 0 = (Q1[0], Q2[0]), slot M/2 = (Q1[M/2], Q2[M/2]) (M even), slot k = Q1[k] and
+// slot M-k = Q2[k] for 0 < k < M/2.  Field 1 = Poisson (barotropic), field 2 = Helmholtz.
+struct Plan {
+    int M, P, ncol;          // ncol = 2M real columns
+    int pow2;                // 1: radix-8 Stockham path, 0: direct DFT path
+    int log2M;
+    int tpr, rpb;            // threads per row, rows per block (pow2 path)
+    int C;                   // 32-row chunks in y
+    int lenLast;             // rows in the last chunk
+    int wpc, CS, m;          // warps per CTA, cluster size, chunks per warp
+    double2* tw;             // exp(-2 pi i n / M), n < M
+    double *rtab, *kap, *rho32, *h32, *rhoL, *hL, *inv1mrP, *pinw;   // per real column
+    double k0scale;          // dx^2 / M
+};
+
+struct FftArgs {
+    Geom g;
+    Plan pl;
+    const double* q1;  // forward: layer-1 / layer-2 PV fields of member 0
+    const double* q2;
+    double* psi1;      // inverse: output fields of member 0
+    double* psi2;
+    double* S;         // spectral rows, member 0
+    int64_t sstride;   // doubles per member in S
+    int64_t mstride;   // doubles per member in q / psi (= 2 * fstride)
+    double A[4];       // forward: P_inv; inverse: P (row-major)
+    const double* scal;  // per member: [0] = sum of the Poisson k=0 column, [1] = gauge
+    int use_gauge;
+};
+
+struct YArgs {
+    Plan pl;
+    double* S;
+    int64_t sstride;
+    double* k0sol;      // per member: P doubles, solution of the singular k=0 Poisson column
+    double* scal;       // per member: 4 doubles
+    int pinned;         // 1: apply the reference's node-(0,0) pin (src/schemes/laplacian.jl:66-75)
+};
+
+struct Handle;
+
+// kernels / launchers (one per translation unit)
+cudaError_t launch_zeta(Handle* h, int timestep);
+cudaError_t launch_fft_forward(Handle* h, const double* q_fields, int which_pinv);
+cudaError_t launch_fft_inverse(Handle* h, double* psi_fields, int use_gauge);
+cudaError_t launch_ysolve(Handle* h, int pinned, int do_poisson_only);
+cudaError_t launch_unpack(Handle* h, const double* host_like, double* dev_fields, int slot_of_level0,
+                          int nlevels);
+cudaError_t launch_pack(Handle* h, const double* dev_fields, double* host_like, int cur);
+cudaError_t launch_diag(Handle* h);
+cudaError_t build_plan(Handle* h);
+void free_plan(Handle* h);
+
+struct Handle {
+    qg_params prm;
+    int device = 0;
+    int nm = 1;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    Geom g;
+    int nfields = 0;                 // 3 * nm * 2
+    double* q = nullptr;             // [3 slots][nm][2] fields
+    double* psi = nullptr;
+    double* f = nullptr;
+    int qcur = 0;                    // slot of the newest level of q and f_store
+    int pcur = 0;                    // slot of the newest level of psi
+    bool have_state = false;
+    CUtensorMap tm_q, tm_psi;
+    Plan plan;
+    bool plan_ok = false;
+    double* S = nullptr;             // spectral scratch [nm][P][2M]
+    double* k0sol = nullptr;         // [nm][P]
+    double* scal = nullptr;          // [nm][4]
+    double* stage = nullptr;         // host-layout staging (3*2*(M+2)*(P+2)*nm doubles)
+    double* diag_part = nullptr;     // partial sums for diagnostics
+    int diag_blocks = 0;
+    int64_t launches = 0;
+    int profiling = 0;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    double kms[QG_NKERNELS] = {0};
+    int64_t kcount[QG_NKERNELS] = {0};
+    std::string err;
+
+    double* field(double* base, int slot, int member, int layer) const {
+        return base + ((int64_t)(slot * nm + member) * 2 + layer) * g.fstride;
+    }
+    int zindex(int slot, int member, int layer) const { return (slot * nm + member) * 2 + layer; }
+};
+
+// Wraps a kernel launch with optional CUDA-event timing on the handle's stream.
+struct KernelTimer {
+    Handle* h;
+    int id;
+    KernelTimer(Handle* h_, int id_) : h(h_), id(id_) {
+        if (h->profiling) cudaEventRecord(h->ev0, h->stream);
+    }
+    ~KernelTimer() {
+        h->launches++;
+        h->kcount[id]++;
+        if (h->profiling) {
+            cudaEventRecord(h->ev1, h->stream);
+            cudaEventSynchronize(h->ev1);
+            float ms = 0.f;
+            cudaEventElapsedTime(&ms, h->ev0, h->ev1);
+            h->kms[id] += ms;
+        }
+    }
+};
+
+#ifdef __CUDACC__
+// ---- block-wide helpers (blockDim.x == 1024) -----------------------------------------
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// deterministic block sum, result broadcast to all threads
+__device__ __forceinline__ double block_sum(double v, double* sh) {
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    v = warp_sum(v);
+    __syncthreads();
+    if (lane == 0) sh[w] = v;
+    __syncthreads();
+    double t = 0.0;
+    for (int i = 0; i < nw; ++i) t += sh[i];
+    return t;
+}
+
+// exclusive prefix over threads of per-thread totals
+__device__ __forceinline__ double block_exclusive_scan(double v, double* sh) {
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    double inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const double n = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += n;
+    }
+    __syncthreads();
+    if (lane == 31) sh[w] = inc;
+    __syncthreads();
+    double base = 0.0;
+    for (int i = 0; i < w && i < nw; ++i) base += sh[i];
+    return base + inc - v;
+}
+
+#endif
+
+}  // namespace qg
+
+struct qg_handle : public qg::Handle {};

@@ -1,0 +1,112 @@
+"""CPU-side checks of the host shim and of the C-ABI library: it loads, exports every symbol
+include/qgb200.h declares, refuses to run without a GPU (no CPU fallback), and the host
+mirror evaluates the reference's parameter algebra exactly."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+import qgb200
+from qgb200 import _lib
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _ensure_built():
+    if not os.path.exists(_lib.LIB_PATH):
+        import __graft_entry__
+        __graft_entry__.build()
+
+
+def header_functions():
+    src = open(os.path.join(ROOT, "include", "qgb200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(qg_[a-z_0-9]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol():
+    _ensure_built()
+    names = header_functions()
+    assert len(names) >= 17
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    for n in names:
+        assert hasattr(lib, n), f"libqgb200.so does not export {n}"
+    assert sorted(_lib.SYMBOLS) == names, "python binding table and header disagree"
+    assert qgb200.load().qg_abi_version() == 1
+
+
+def test_param_struct_matches_header_layout():
+    # int32 M, P; 8 doubles; 2x double[4]; 3 doubles
+    assert ctypes.sizeof(qgb200.qg_params) == 8 + 8 * 8 + 2 * 32 + 3 * 8
+    assert qgb200.qg_params.dx.offset == 8 and qgb200.qg_params.Pinv.offset == 72
+
+
+def test_no_gpu_means_loud_failure(have_gpu):
+    _ensure_built()
+    if have_gpu:
+        pytest.skip("GPU present")
+    m = qgb200.BaroclinicModel(1000., 2000., 2e-11, 4e6, 4e6, 3600., 86400., 0.1, 16, 16, 4e6 / 16, 100., 1e-7, 4e4, 1e-6)
+    with pytest.raises(qgb200.QGError) as ei:
+        qgb200.Session(m)
+    assert ei.value.code == -4 and "no CPU fallback" in ei.value.message
+
+
+def test_create_rejects_bad_arguments():
+    _ensure_built()
+    lib = qgb200.load()
+    m = qgb200.BaroclinicModel(1000., 2000., 2e-11, 4e6, 4e6, 3600., 86400., 0.1, 2, 16, 4e6 / 16, 100., 1e-7, 4e4, 1e-6)
+    p = qgb200.make_params(m)
+    h = ctypes.c_void_p()
+    assert lib.qg_create(ctypes.byref(p), 0, 1, None, ctypes.byref(h)) == -1
+    assert b"M and P" in lib.qg_last_error(None)
+    assert lib.qg_create(None, 0, 1, None, ctypes.byref(h)) == -1
+    assert lib.qg_step(None, 1, 1) == -1 and lib.qg_destroy(None) == 0
+
+
+def test_parameter_mirror_is_exact():
+    """src/test.jl:8-44 on the product's host mirror."""
+    m = qgb200.BaroclinicModel(1.0 * qgb200.KM, 2.0 * qgb200.KM, 2e-11, 4000.0 * qgb200.KM, 4000.0 * qgb200.KM,
+                               15.0 * qgb200.MINUTES, 0.5 * qgb200.YEAR, 2.0, 128, 128, 4000.0 * qgb200.KM / 128,
+                               100.0, 1e-7, 40.0 * qgb200.KM, 1e-2)
+    ratio = 0.5 * (1000 + 2000) / (40000 ** 2 * (1 / 1000 + 1 / 2000))
+    assert qgb200.ratio_term(m) == ratio
+    assert qgb200.S1_plus(m) == 2 * ratio / (1000 * 3000)
+    assert qgb200.S2_minus(m) == 2 * ratio / (2000 * 3000)
+    assert qgb200.beta_1(m) == m.beta + qgb200.S1_plus(m) * m.U
+    assert qgb200.beta_2(m) == m.beta - qgb200.S2_minus(m) * m.U
+    assert qgb200.S_eig(m) == -1 / m.R_d ** 2 == (-qgb200.S1_plus(m) - qgb200.S2_minus(m))
+    assert np.array_equal(qgb200.P_matrix(m.H_1, m.H_2) @ qgb200.P_inv_matrix(m), np.eye(2))
+    assert m.H == 3000.0 and m.domain == qgb200.RectangularDomain(0.0, m.Lx, 0.0, m.Ly)
+    p = qgb200.make_params(m)
+    assert list(p.Pfwd) == [1.0, -1.0, 1.0, 1.0]          # P_matrix(H_1, H_1), src/model.jl:173
+    assert list(p.Pinv) == list(qgb200.P_inv_matrix(m).ravel())
+    assert (p.beta1, p.beta2, p.alpha) == (qgb200.beta_1(m), qgb200.beta_2(m), qgb200.S_eig(m))
+    with pytest.raises(AttributeError):
+        m.dt = 1.0
+
+
+def test_host_mirror_matches_oracle_initial_condition():
+    import qg_oracle as o
+    mo = o.standard_model(12, 9)
+    mg = qgb200.BaroclinicModel(mo.H_1, mo.H_2, mo.beta, mo.Lx, mo.Ly, mo.dt, mo.T, mo.U, mo.M, mo.P, mo.dx,
+                                mo.visc, mo.r, mo.R_d, mo.initial_kick)
+    zo, po = o.initialise_model(mo, seed=5)
+    zg, pg = qgb200.initialise_model(mg, seed=5)
+    assert np.array_equal(zo, zg) and np.array_equal(po, pg)
+    bad = qgb200.BaroclinicModel(1000.0, 2000.0, 2e-11, 4e6, 4e6, 60.0, 600.0, 0.0, 8, 8, 5e5, 100.0, 1e-7, 4e4, 1e-6)
+    with pytest.raises(AssertionError):
+        qgb200.initialise_model(bad)
+
+
+def test_plan_tokens_and_argument_checks():
+    m = qgb200.BaroclinicModel(1000., 2000., 2e-11, 4e6, 4e6, 3600., 86400., 0.1, 16, 16, 4e6 / 16, 100., 1e-7, 4e4, 1e-6)
+    pc = qgb200.get_poisson_cholesky(16, 16, m.dx)
+    hc = qgb200.get_helmholtz_cholesky(16, 16, m.dx, qgb200.S_eig(m))
+    assert pc.pinned and not hc.pinned
+    z = np.zeros((18, 18, 2, 3), order="F")
+    with pytest.raises(TypeError):
+        qgb200.evolve_psi(m, z, z.copy(order="F"), hc, pc)   # swapped plans
+    with pytest.raises(ValueError):
+        qgb200.evolve_psi(m, z, z.copy(order="F"), pc, qgb200.get_helmholtz_cholesky(16, 16, m.dx, -1.0))

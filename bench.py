@@ -1,0 +1,282 @@
+#!/usr/bin/env python
+"""bench.py — grid-cell·steps/s of the two-layer QG step on B200 (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--grid M P]
+
+A "step" is one pass of the hot path (evolve_zeta! + evolve_psi!, reference
+src/run_model_no_output.jl:10-13) over the whole grid.  N = 1 runs BASELINE.json config 3, the
+4096 x 4096 headline grid (dt = 5 min).  N > 1 (torchrun, one rank per
+GPU) runs one independent 4096 x 4096 run per GPU — member-per-GPU ensemble sharding, no
+data-path collective, weak scaling; timing is max over ranks.
+
+value  : cell·steps/s with the state resident in HBM, K steps between CUDA events.
+e2e    : the same metric through the public host API on pinned HOST buffers: upload of the
+         reference-layout state arrays, K steps, download of (zeta, psi) — the
+         run_model_no_output call pattern — all inside the timed region.
+roofline: the dominant kernel's algorithmic bytes / its CUDA-event duration measured inside
+         the timed region, against MEASURED_PEAKS.json hbm_gbs.
+cpu_baseline / --impl reference: the C restatement of the reference algorithm
+         (oracle/qg_oracle.c, OpenMP, all host threads) on a bounded sample of the same grid.
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(ROOT, "julia-ocean-modelling_b200", "python"))
+
+METRIC = "grid-cell·steps/s, Phillips 2-layer QG at 4096²"
+UNIT = "cell·steps/s"
+# algorithmic bytes per cell per launch (DESIGN.md "Roofline accounting")
+KERNEL_BYTES = {"k1_zeta_step": 96.0, "k2_fft_forward": 32.0, "k3_ysolve": 32.0, "k4_fft_inverse": 32.0}
+STEP_BYTES = 128.0   # implementation-independent compulsory traffic per cell·step
+
+
+def model_args(M, P):
+    """The reference's parameter block (src/benchmarking/benchmarking.jl:6-18) on the
+    benchmark grids; dt per SURVEY.md 8d (stable explicit viscosity)."""
+    KM, MIN = 1000.0, 60.0
+    Lx = 4000.0 * KM
+    dx = Lx / M
+    Ly = dx * P
+    dt = 60.0 * MIN if M <= 1024 else (5.0 * MIN if M <= 4096 else 30.0)
+    return dict(H_1=1.0 * KM, H_2=2.0 * KM, beta=2e-11, Lx=Lx, Ly=Ly, dt=dt, T=86400.0, U=0.1, M=M, P=P, dx=dx,
+                visc=100.0, r=1e-7, R_d=40.0 * KM, initial_kick=1e-6)
+
+
+def peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured"
+    except Exception:
+        return 6650.0, "fallback"
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock and throttle reasons of one GPU through NVML while the timed region runs."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.stop_flag, self.samples, self.reasons, self.max_mhz = index, False, [], set(), None
+
+    def run(self):
+        try:
+            import pynvml as nv
+            nv.nvmlInit()
+            h = nv.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_mhz = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+            names = {"hw_slowdown": 0x8, "sw_power_cap": 0x4, "hw_thermal_slowdown": 0x40,
+                     "sw_thermal_slowdown": 0x20, "hw_power_brake": 0x80}
+            while not self.stop_flag:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
+                try:
+                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
+                except Exception:
+                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                for k, bit in names.items():
+                    if r & bit:
+                        self.reasons.add(k)
+                time.sleep(0.02)
+        except Exception as e:   # NVML missing: report that instead of inventing numbers
+            self.reasons.add(f"nvml_unavailable:{type(e).__name__}")
+
+    def result(self):
+        s = sorted(self.samples)
+        return {"sm_mhz": (s[len(s) // 2] if s else None), "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(s)}
+
+
+def cpu_reference_leg(M, P, steps, warmup, budget_s=25.0):
+    """Times oracle/qg_oracle.c (the reference algorithm restated in C, OpenMP on all host
+    threads) on the same grid for a bounded number of steps."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import numpy as np
+    import qg_oracle as o
+    import qg_oracle_c as oc
+    a = model_args(M, P)
+    m = o.make_model(*[a[k] for k in ("H_1", "H_2", "beta", "Lx", "Ly", "dt", "T", "U", "M", "P", "dx", "visc", "r",
+                                      "R_d", "initial_kick")])
+    zeta, psi = o.initialise_model(m, seed=1)
+    f = np.zeros_like(zeta)
+    threads = oc.max_threads()
+    t = 1
+    w = max(1, min(warmup, 1))
+    t0 = time.perf_counter()
+    oc.run_steps(m, zeta, psi, f, t, w, threads)
+    per = (time.perf_counter() - t0) / w
+    t += w
+    n = int(max(1, min(steps, budget_s / max(per, 1e-9))))
+    t0 = time.perf_counter()
+    oc.run_steps(m, zeta, psi, f, t, n, threads)
+    dt = time.perf_counter() - t0
+    return {"value": M * P * n / dt, "unit": UNIT, "cores": threads, "kind": "port",
+            "sample": f"{n} steps of the same {M}x{P} grid after {w} warm-up (C/OpenMP restatement, spectral "
+                      f"solve standing in for CHOLMOD), {dt / n * 1e3:.1f} ms/step"}, dt / n * 1e3, n
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    M, P = args.grid
+    cb, ms, n = cpu_reference_leg(M, P, args.steps, args.warmup, budget_s=60.0)
+    line = {"metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": n,
+            "warmup": 1, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic", "impl": "reference",
+            "config": {"workload": f"Phillips two-layer {M}x{P}, Float64, reference algorithm on host cores "
+                                   f"(C restatement; Julia is not installed in this image)"},
+            "cpu_baseline": cb,
+            "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200")
+    ap.add_argument("--grid", type=int, nargs=2, default=[4096, 4096])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    args.warmup = max(args.warmup, 3)
+
+    import numpy as np
+    import torch
+    import qgb200
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the b200 arm has no CPU fallback (use --impl reference)")
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    M, P = args.grid
+    a = model_args(M, P)
+    model = qgb200.BaroclinicModel(*[a[k] for k in ("H_1", "H_2", "beta", "Lx", "Ly", "dt", "T", "U", "M", "P", "dx",
+                                                    "visc", "r", "R_d", "initial_kick")])
+    K, W = args.steps, args.warmup
+    # synthetic "randomly perturbed jet": seeded white-noise psi on the uniform shear U (rank = member)
+    zeta, psi = qgb200.initialise_model(model, seed=1 + rank)
+    n_elem = zeta.size
+    pin = [torch.empty(n_elem, dtype=torch.float64).pin_memory() for _ in range(3)]
+    views = [p.numpy().reshape(zeta.shape, order="F") for p in pin]
+    views[0][...] = zeta
+    views[1][...] = psi
+    views[2][...] = 0.0
+    del zeta, psi
+
+    # a dedicated (non-default) stream shared by torch's events and the library's launches
+    stream = torch.cuda.Stream()
+    torch.cuda.set_stream(stream)
+    sess = qgb200.Session(model, members=1, device=local_rank, stream=stream.cuda_stream)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident timing ("value") --------------------------------------------------
+    sess.upload_raw(pin[0].data_ptr(), pin[1].data_ptr(), pin[2].data_ptr())
+    sess.step(1, W)
+    sampler = ClockSampler(local_rank)
+    barrier()
+    sampler.start()
+    sess.set_profiling(True)
+    l0 = sess.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    sess.step(W + 1, K)
+    e1.record(stream)
+    barrier()
+    ms_total = e0.elapsed_time(e1)
+    launches = sess.launch_count() - l0
+    ktimes = sess.kernel_times()
+    sess.set_profiling(False)
+    sampler.stop_flag = True
+    sampler.join(timeout=2.0)
+    E, Z = sess.diagnostics()
+    if not (np.isfinite(E) and np.isfinite(Z)):
+        raise SystemExit("bench.py: state went non-finite during the timed region")
+
+    # ---- end-to-end timing through host buffers ("e2e") -------------------------------------
+    views[2][...] = 0.0
+    zeta0, psi0 = qgb200.initialise_model(model, seed=1 + rank)
+    views[0][...] = zeta0
+    views[1][...] = psi0
+    del zeta0, psi0
+    Ke = K
+    barrier()
+    t0 = time.perf_counter()
+    sess.upload_raw(pin[0].data_ptr(), pin[1].data_ptr(), pin[2].data_ptr())
+    sess.step(1, Ke)
+    sess.download_raw(pin[0].data_ptr(), pin[1].data_ptr(), 0)
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    h2d = 3 * n_elem * 8
+    d2h = 2 * n_elem * 8
+
+    tmax = torch.tensor([ms_total, e2e_s * 1e3], dtype=torch.float64, device="cuda")
+    if dist is not None:
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+    ms_total, e2e_ms = float(tmax[0]), float(tmax[1])
+    sess.close()
+
+    if rank == 0:
+        cells = float(M) * P
+        value = world * cells * K / (ms_total * 1e-3)
+        e2e_value = world * cells * Ke / (e2e_ms * 1e-3)
+        peak, peak_src = peaks()
+        per = {k: (ms / n * 1e-3 if n else 0.0) for k, (ms, n) in ktimes.items()}
+        dom = max(KERNEL_BYTES, key=lambda k: per.get(k, 0.0))
+        ach = KERNEL_BYTES[dom] * cells / per[dom] / 1e9
+        kern = {k: {"us": round(per[k] * 1e6, 2), "GBps": round(KERNEL_BYTES[k] * cells / per[k] / 1e9, 1),
+                    "frac": round(KERNEL_BYTES[k] * cells / per[k] / 1e9 / peak, 4)}
+                for k in KERNEL_BYTES if per.get(k)}
+        small = {k: round(per[k] * 1e6, 2) for k in per if k not in KERNEL_BYTES and per[k]}
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"Phillips two-layer {M}x{P}, Float64, "
+                                   + ("single B200 (BASELINE.json config 3, headline roofline run)" if world == 1 else
+                                      f"{world} independent members, one per B200 (ensemble sharding, no collective)"),
+                       "dt_s": a["dt"], "ic": "seeded uniform psi noise on shear U (initialise_model), seed 1+rank",
+                       "l2": "working set 2.7 GB per GPU >> 126 MB L2, no explicit flush",
+                       "parallelism": f"member-per-gpu x{world}"},
+            "roofline": {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s",
+                         "frac": ach / peak, "traffic": None, "peak_source": peak_src,
+                         "algorithmic_bytes_per_cell": KERNEL_BYTES[dom],
+                         "step": {"achieved": STEP_BYTES * cells * K / (ms_total * 1e-3) / 1e9,
+                                  "frac": STEP_BYTES * cells * K / (ms_total * 1e-3) / 1e9 / peak,
+                                  "algorithmic_bytes_per_cell_step": STEP_BYTES},
+                         "kernels": kern, "small_kernels_us": small},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d / Ke, "d2h_bytes_per_step": d2h / Ke,
+                    "what": f"pinned host arrays -> qg_upload_state -> qg_step({Ke}) -> qg_download_state(zeta, psi)",
+                    "ms_total": e2e_ms},
+            "gpu_launches": int(launches),
+            "clocks": sampler.result(),
+            "diagnostics": {"E": float(E), "Z": float(Z)},
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            cb, _, _ = cpu_reference_leg(M, P, 4, 1, budget_s=20.0)
+            line["cpu_baseline"] = cb
+        print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -15,8 +15,13 @@
 //
 // The transform is a hand-written Stockham autosort FFT: 8 points per thread, radix-8
 // passes (plus one radix-4/2 pass when log2 M is not a multiple of 3), data exchanged
-// through XOR-swizzled shared memory, the first pass fed straight from global memory.
-// Twiddles come from a table evaluated in extended precision on the host.
+// through XOR-swizzled shared memory between passes only: the first pass is fed straight
+// from global memory and the inverse transform's last pass stores straight to global
+// memory (its outputs are coalesced by construction).  The kernels are persistent: a CTA
+// loops over rows, and each thread keeps one base twiddle per pass in registers for the
+// whole launch (the twiddle depends on the thread's position, not on the row) and derives
+// the powers w^2..w^7 by multiplication, so the row loop issues no twiddle loads at all.
+// The base twiddles come from a table evaluated in extended precision on the host.
 // Non-power-of-two M (the reference benchmarks M = 8:8:128) takes a direct O(M^2) DFT
 // path with the same spectral layout.
 #include "qg_internal.cuh"
@@ -62,198 +67,278 @@ __device__ __forceinline__ void bfly8(double2 (&a)[8]) {
     double2 b1 = cadd(a[1], a[5]), b5 = csub(a[1], a[5]);
     double2 b2 = cadd(a[2], a[6]), b6 = csub(a[2], a[6]);
     double2 b3 = cadd(a[3], a[7]), b7 = csub(a[3], a[7]);
-    // odd half: multiply by W8^t, W8 = exp(SIGN * i pi / 4)
     {
-        // W8^1 = h (1 + SIGN i)
-        const double2 t5 = muli<SIGN>(b5);
+        const double2 t5 = muli<SIGN>(b5);   // W8^1 = h (1 + SIGN i)
         b5 = make_double2(h * (b5.x + t5.x), h * (b5.y + t5.y));
-        b6 = muli<SIGN>(b6);
-        // W8^3 = h (-1 + SIGN i)
-        const double2 t7 = muli<SIGN>(b7);
+        b6 = muli<SIGN>(b6);                 // W8^2 = SIGN i
+        const double2 t7 = muli<SIGN>(b7);   // W8^3 = h (-1 + SIGN i)
         b7 = make_double2(h * (t7.x - b7.x), h * (t7.y - b7.y));
     }
-    bfly4<SIGN>(b0, b1, b2, b3);   // even outputs X[0], X[2], X[4], X[6]
-    bfly4<SIGN>(b4, b5, b6, b7);   // odd outputs  X[1], X[3], X[5], X[7]
+    bfly4<SIGN>(b0, b1, b2, b3);   // X[0], X[2], X[4], X[6]
+    bfly4<SIGN>(b4, b5, b6, b7);   // X[1], X[3], X[5], X[7]
     a[0] = b0; a[2] = b1; a[4] = b2; a[6] = b3;
     a[1] = b4; a[3] = b5; a[5] = b6; a[7] = b7;
 }
 
-// Stockham FFT of one row of N = 8 * tpr points held 8 per thread: on entry
-// v[t] = x[lt + t * tpr]; on exit the transform is in shared memory `s` (swizzled,
-// natural order) and a __syncthreads() has been executed.
-template <int SIGN>
-__device__ __forceinline__ void fft_row(double2 (&v)[8], double2* s, int N, int log2N, int tpr, int lt,
-                                        const double2* __restrict__ tw) {
-    const int nb8 = log2N / 3;
-    const int rem = log2N - 3 * nb8;
-    int Ns = 1;
-    for (int p = 0; p < nb8; ++p) {
-        if (p > 0) {
-            __syncthreads();
+// Per-thread FFT engine for rows of N = 2^LOG2N points, 8 points per thread.
+template <int LOG2N, int SIGN>
+struct RowFft {
+    static constexpr int N = 1 << LOG2N;
+    static constexpr int TPR = N / 8;
+    static constexpr int NB8 = LOG2N / 3;
+    static constexpr int REM = LOG2N % 3;
+    static constexpr int NW8 = NB8 > 1 ? NB8 - 1 : 1;
+    double2 w8[NW8];   // base twiddle of radix-8 pass p = 1 .. NB8-1
+    double2 wr[4];     // base twiddles of the remainder pass (2 butterflies radix-4, 4 radix-2)
+
+    __device__ __forceinline__ void init(const double2* __restrict__ tw, int lt) {
+        int Ns = 8;
 #pragma unroll
-            for (int t = 0; t < 8; ++t) v[t] = s[swz(lt + t * tpr)];
-            __syncthreads();
+        for (int p = 1; p < NB8; ++p) {
             const int k = lt & (Ns - 1);
-            const int step = N / (Ns * 8);
-#pragma unroll
-            for (int t = 1; t < 8; ++t) v[t] = cmul(v[t], twid<SIGN>(tw, t * k * step));
+            w8[p - 1] = twid<SIGN>(tw, k * (N / (Ns * 8)));
+            Ns *= 8;
         }
-        bfly8<SIGN>(v);
-        const int k = lt & (Ns - 1);
-        const int j0 = (lt - k) * 8 + k;
+        if (REM == 2) {
 #pragma unroll
-        for (int u = 0; u < 8; ++u) s[swz(j0 + u * Ns)] = v[u];
-        Ns *= 8;
-    }
-    if (rem == 2) {   // one radix-4 pass, two butterflies per thread
-        __syncthreads();
+            for (int b = 0; b < 2; ++b) {
+                const int j = lt + b * TPR;
+                wr[b] = twid<SIGN>(tw, (j & (Ns - 1)) * (N / (Ns * 4)));
+            }
+        } else if (REM == 1) {
 #pragma unroll
-        for (int b = 0; b < 2; ++b) {
-            const int j = lt + b * tpr;
-#pragma unroll
-            for (int t = 0; t < 4; ++t) v[b * 4 + t] = s[swz(j + t * 2 * tpr)];
-        }
-        __syncthreads();
-#pragma unroll
-        for (int b = 0; b < 2; ++b) {
-            const int j = lt + b * tpr;
-            const int k = j & (Ns - 1);
-            const int step = N / (Ns * 4);
-#pragma unroll
-            for (int t = 1; t < 4; ++t) v[b * 4 + t] = cmul(v[b * 4 + t], twid<SIGN>(tw, t * k * step));
-            bfly4<SIGN>(v[b * 4 + 0], v[b * 4 + 1], v[b * 4 + 2], v[b * 4 + 3]);
-            const int j0 = (j - k) * 4 + k;
-#pragma unroll
-            for (int u = 0; u < 4; ++u) s[swz(j0 + u * Ns)] = v[b * 4 + u];
-        }
-    } else if (rem == 1) {   // one radix-2 pass, four butterflies per thread
-        __syncthreads();
-#pragma unroll
-        for (int b = 0; b < 4; ++b) {
-            const int j = lt + b * tpr;
-            v[b * 2 + 0] = s[swz(j)];
-            v[b * 2 + 1] = s[swz(j + 4 * tpr)];
-        }
-        __syncthreads();
-#pragma unroll
-        for (int b = 0; b < 4; ++b) {
-            const int j = lt + b * tpr;
-            const int k = j & (Ns - 1);
-            const int step = N / (Ns * 2);
-            const double2 w = cmul(v[b * 2 + 1], twid<SIGN>(tw, k * step));
-            const double2 x0 = cadd(v[b * 2], w), x1 = csub(v[b * 2], w);
-            const int j0 = (j - k) * 2 + k;
-            s[swz(j0)] = x0;
-            s[swz(j0 + Ns)] = x1;
+            for (int b = 0; b < 4; ++b) {
+                const int j = lt + b * TPR;
+                wr[b] = twid<SIGN>(tw, (j & (Ns - 1)) * (N / (Ns * 2)));
+            }
         }
     }
-    __syncthreads();
+
+    // On entry v[t] = x[lt + t*TPR].  TO_SMEM: on exit the transform sits in `s` (swizzled,
+    // natural order) after a __syncthreads().  Otherwise the last pass stays in registers:
+    //   REM == 0: v[u]       = X[lt + u*TPR]
+    //   REM == 2: v[4b + u]  = X[lt + b*TPR + u*N/4]
+    //   REM == 1: v[2b + u]  = X[lt + b*TPR + u*N/2]
+    template <bool TO_SMEM>
+    __device__ __forceinline__ void run(double2 (&v)[8], double2* s, int lt) {
+        int Ns = 1;
+#pragma unroll
+        for (int p = 0; p < NB8; ++p) {
+            if (p > 0) {
+                __syncthreads();
+#pragma unroll
+                for (int t = 0; t < 8; ++t) v[t] = s[swz(lt + t * TPR)];
+                const double2 w1 = w8[p - 1];
+                const double2 w2 = cmul(w1, w1), w3 = cmul(w2, w1), w4 = cmul(w2, w2);
+                v[1] = cmul(v[1], w1);
+                v[2] = cmul(v[2], w2);
+                v[3] = cmul(v[3], w3);
+                v[4] = cmul(v[4], w4);
+                v[5] = cmul(v[5], cmul(w4, w1));
+                v[6] = cmul(v[6], cmul(w3, w3));
+                v[7] = cmul(v[7], cmul(w4, w3));
+            }
+            bfly8<SIGN>(v);
+            const bool last = (p == NB8 - 1) && REM == 0;
+            if (!last || TO_SMEM) {
+                if (p > 0) __syncthreads();   // every thread has loaded its inputs of this pass
+                const int k = lt & (Ns - 1);
+                const int j0 = (lt - k) * 8 + k;
+#pragma unroll
+                for (int u = 0; u < 8; ++u) s[swz(j0 + u * Ns)] = v[u];
+            }
+            Ns *= 8;
+        }
+        if (REM == 2) {
+            __syncthreads();
+#pragma unroll
+            for (int b = 0; b < 2; ++b)
+#pragma unroll
+                for (int t = 0; t < 4; ++t) v[b * 4 + t] = s[swz(lt + b * TPR + t * 2 * TPR)];
+#pragma unroll
+            for (int b = 0; b < 2; ++b) {
+                const double2 w1 = wr[b], w2 = cmul(w1, w1);
+                v[b * 4 + 1] = cmul(v[b * 4 + 1], w1);
+                v[b * 4 + 2] = cmul(v[b * 4 + 2], w2);
+                v[b * 4 + 3] = cmul(v[b * 4 + 3], cmul(w2, w1));
+                bfly4<SIGN>(v[b * 4 + 0], v[b * 4 + 1], v[b * 4 + 2], v[b * 4 + 3]);
+            }
+            if (TO_SMEM) {
+                __syncthreads();
+#pragma unroll
+                for (int b = 0; b < 2; ++b)
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) s[swz(lt + b * TPR + u * Ns)] = v[b * 4 + u];   // Ns == N/4
+            }
+        } else if (REM == 1) {
+            __syncthreads();
+#pragma unroll
+            for (int b = 0; b < 4; ++b) {
+                v[b * 2 + 0] = s[swz(lt + b * TPR)];
+                v[b * 2 + 1] = s[swz(lt + b * TPR + 4 * TPR)];
+            }
+#pragma unroll
+            for (int b = 0; b < 4; ++b) {
+                const double2 w = cmul(v[b * 2 + 1], wr[b]);
+                const double2 x0 = cadd(v[b * 2], w), x1 = csub(v[b * 2], w);
+                v[b * 2] = x0;
+                v[b * 2 + 1] = x1;
+            }
+            if (TO_SMEM) {
+                __syncthreads();
+#pragma unroll
+                for (int b = 0; b < 4; ++b) {
+                    s[swz(lt + b * TPR)] = v[b * 2];
+                    s[swz(lt + b * TPR + Ns)] = v[b * 2 + 1];   // Ns == N/2
+                }
+            }
+        }
+        if (TO_SMEM) __syncthreads();
+    }
+
+    // index of register slot e (0..7) of the last pass in the output row (see run<false>)
+    static __device__ __forceinline__ int out_index(int lt, int e) {
+        if (REM == 0) return lt + e * TPR;
+        if (REM == 2) return lt + (e >> 2) * TPR + (e & 3) * (N / 4);
+        return lt + (e >> 1) * TPR + (e & 1) * (N / 2);
+    }
+};
+
+template <int LOG2N>
+struct FftLaunch {
+    static constexpr int N = 1 << LOG2N;
+    static constexpr int TPR = N / 8;
+    static constexpr int RPB = TPR >= 128 ? 1 : 128 / TPR;
+    static constexpr int THREADS = TPR * RPB;
+    static constexpr int MINB = THREADS >= 1024 ? 1 : (THREADS >= 512 ? 2 : (THREADS >= 256 ? 4 : 6));
+    static constexpr size_t SMEM = (size_t)RPB * N * sizeof(double2);
+};
+
+// ---------------------------------------------------------------------------------------
+// Forward kernel (persistent): row groups of RPB rows, grid-stride over (member, group).
+// ---------------------------------------------------------------------------------------
+template <int LOG2N>
+__global__ void __launch_bounds__(FftLaunch<LOG2N>::THREADS, FftLaunch<LOG2N>::MINB)
+k2_fft_forward(const FftArgs a, int ngroups_per_member, int ngroups_total) {
+    using L = FftLaunch<LOG2N>;
+    using F = RowFft<LOG2N, -1>;
+    extern __shared__ __align__(16) double2 fft_smem[];
+    constexpr int N = L::N, TPR = L::TPR;
+    const int lr = threadIdx.x / TPR, lt = threadIdx.x % TPR;
+    double2* s = fft_smem + (size_t)lr * N;
+    F fft;
+    fft.init(a.pl.tw, lt);
+    const double A0 = a.A[0], A1 = a.A[1], A2 = a.A[2], A3 = a.A[3];
+
+    for (int grp = blockIdx.x; grp < ngroups_total; grp += gridDim.x) {
+        const int member = grp / ngroups_per_member;
+        const int row = (grp - member * ngroups_per_member) * L::RPB + lr;
+        const bool live = row < a.pl.P;
+        const double* __restrict__ q1 = a.q1 + member * a.mstride + a.g.at(0, live ? row : 0);
+        const double* __restrict__ q2 = a.q2 + member * a.mstride + a.g.at(0, live ? row : 0);
+        double x1[8], x2[8];
+#pragma unroll
+        for (int t = 0; t < 8; ++t) {
+            x1[t] = __ldg(q1 + lt + t * TPR);
+            x2[t] = __ldg(q2 + lt + t * TPR);
+        }
+        double2 v[8];
+#pragma unroll
+        for (int t = 0; t < 8; ++t)
+            v[t] = make_double2(A0 * x1[t] + A1 * x2[t], A2 * x1[t] + A3 * x2[t]);   // src/model.jl:180
+        fft.template run<true>(v, s, lt);
+        if (live) {
+            double2* __restrict__ out =
+                reinterpret_cast<double2*>(a.S + member * a.sstride + (int64_t)row * a.pl.ncol);
+            constexpr int half = N >> 1;
+#pragma unroll
+            for (int b = 0; b < 4; ++b) {
+                const int k = lt + b * TPR;   // 0 .. N/2 - 1
+                if (k == 0) {
+                    out[0] = s[swz(0)];
+                    out[half] = s[swz(half)];
+                } else {
+                    const double2 X = s[swz(k)], Y = s[swz(N - k)];
+                    out[k] = make_double2(0.5 * (X.x + Y.x), 0.5 * (X.y - Y.y));        // Q1[k]
+                    out[N - k] = make_double2(0.5 * (X.y + Y.y), 0.5 * (Y.x - X.x));    // Q2[k]
+                }
+            }
+        }
+        __syncthreads();   // the row buffer is reused by the next group
+    }
 }
 
 // ---------------------------------------------------------------------------------------
-// Forward kernel, power-of-two M >= 8.  Block = rpb rows x tpr threads, grid = (rows, members).
+// Inverse kernel (persistent).
 // ---------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(1024)
-k2_fft_forward(const FftArgs a) {
+template <int LOG2N>
+__global__ void __launch_bounds__(FftLaunch<LOG2N>::THREADS, FftLaunch<LOG2N>::MINB)
+k4_fft_inverse(const FftArgs a, int ngroups_per_member, int ngroups_total) {
+    using L = FftLaunch<LOG2N>;
+    using F = RowFft<LOG2N, +1>;
     extern __shared__ __align__(16) double2 fft_smem[];
-    const int N = a.pl.M, tpr = a.pl.tpr;
-    const int lr = threadIdx.x / tpr, lt = threadIdx.x - lr * tpr;
-    const int row = blockIdx.x * a.pl.rpb + lr;
-    const bool live = row < a.pl.P;
-    const int member = blockIdx.y;
+    constexpr int N = L::N, TPR = L::TPR;
+    const int lr = threadIdx.x / TPR, lt = threadIdx.x % TPR;
     double2* s = fft_smem + (size_t)lr * N;
-    const double* __restrict__ q1 = a.q1 + member * a.mstride + a.g.at(0, live ? row : 0);
-    const double* __restrict__ q2 = a.q2 + member * a.mstride + a.g.at(0, live ? row : 0);
-
-    double2 v[8];
-#pragma unroll
-    for (int t = 0; t < 8; ++t) {
-        const int n = lt + t * tpr;
-        const double x1 = live ? __ldg(q1 + n) : 0.0, x2 = live ? __ldg(q2 + n) : 0.0;
-        v[t] = make_double2(a.A[0] * x1 + a.A[1] * x2, a.A[2] * x1 + a.A[3] * x2);   // src/model.jl:180
-    }
-    fft_row<-1>(v, s, N, a.pl.log2M, tpr, lt, a.pl.tw);
-
-    if (!live) return;
-    double2* __restrict__ out = reinterpret_cast<double2*>(a.S + member * a.sstride + (int64_t)row * a.pl.ncol);
-    const int half = N >> 1;
-#pragma unroll
-    for (int b = 0; b < 4; ++b) {
-        const int k = lt + b * tpr;   // 0 .. N/2 - 1
-        if (k == 0) {
-            out[0] = s[swz(0)];
-            out[half] = s[swz(half)];
-        } else {
-            const double2 A = s[swz(k)], B = s[swz(N - k)];
-            out[k] = make_double2(0.5 * (A.x + B.x), 0.5 * (A.y - B.y));        // Q1[k]
-            out[N - k] = make_double2(0.5 * (A.y + B.y), 0.5 * (B.x - A.x));    // Q2[k]
-        }
-    }
-}
-
-// ---------------------------------------------------------------------------------------
-// Inverse kernel, power-of-two M >= 8.
-// ---------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(1024)
-k4_fft_inverse(const FftArgs a) {
-    extern __shared__ __align__(16) double2 fft_smem[];
-    const int N = a.pl.M, tpr = a.pl.tpr;
-    const int lr = threadIdx.x / tpr, lt = threadIdx.x - lr * tpr;
-    const int row = blockIdx.x * a.pl.rpb + lr;
-    const bool live = row < a.pl.P;
-    const int member = blockIdx.y;
-    double2* s = fft_smem + (size_t)lr * N;
-    const double2* __restrict__ in =
-        reinterpret_cast<const double2*>(a.S + member * a.sstride + (int64_t)(live ? row : 0) * a.pl.ncol);
-    const int half = N >> 1;
-#pragma unroll
-    for (int b = 0; b < 4; ++b) {
-        const int k = lt + b * tpr;
-        if (k == 0) {
-            s[swz(0)] = __ldg(in);
-            s[swz(half)] = __ldg(in + half);
-        } else {
-            const double2 U1 = __ldg(in + k), U2 = __ldg(in + N - k);
-            s[swz(k)] = make_double2(U1.x - U2.y, U1.y + U2.x);        // U1 + i U2
-            s[swz(N - k)] = make_double2(U1.x + U2.y, U2.x - U1.y);    // conj(U1) + i conj(U2)
-        }
-    }
-    __syncthreads();
-    double2 v[8];
-#pragma unroll
-    for (int t = 0; t < 8; ++t) v[t] = s[swz(lt + t * tpr)];
-    __syncthreads();
-    fft_row<+1>(v, s, N, a.pl.log2M, tpr, lt, a.pl.tw);
-
-    if (!live) return;
-    const double gauge = a.use_gauge ? a.scal[member * 4 + 1] : 0.0;
-    double* __restrict__ p1 = a.psi1 + member * a.mstride;
-    double* __restrict__ p2 = a.psi2 + member * a.mstride;
+    F fft;
+    fft.init(a.pl.tw, lt);
+    const double A0 = a.A[0], A1 = a.A[1], A2 = a.A[2], A3 = a.A[3];
     const int M = a.g.M, P = a.g.P;
     const int64_t dyo = (int64_t)P * a.g.pitch;
-    const bool gb = row < GHOST, gt = row >= P - GHOST;
+    constexpr int half = N >> 1;
+
+    for (int grp = blockIdx.x; grp < ngroups_total; grp += gridDim.x) {
+        const int member = grp / ngroups_per_member;
+        const int row = (grp - member * ngroups_per_member) * L::RPB + lr;
+        const bool live = row < P;
+        const double2* __restrict__ in =
+            reinterpret_cast<const double2*>(a.S + member * a.sstride + (int64_t)(live ? row : 0) * a.pl.ncol);
+        // Z[k] = U1[k] + i U2[k] (k < N/2), Z[N-k] = conj(U1[k]) + i conj(U2[k]); slot k holds
+        // U1[k] and slot N-k holds U2[k]; slots 0 and N/2 hold (real, real) pairs = Z itself.
+        double2 v[8];
 #pragma unroll
-    for (int t = 0; t < 8; ++t) {
-        const int n = lt + t * tpr;
-        const double2 z = s[swz(n)];
-        const double t1 = z.x - gauge;                 // pinned node: psi~1(0,0) = 0
-        const double o1 = a.A[0] * t1 + a.A[1] * z.y;  // src/model.jl:196
-        const double o2 = a.A[2] * t1 + a.A[3] * z.y;
-        const int64_t o = a.g.at(n, row);
-        const bool gl = n < GHOST, gr = n >= M - GHOST;
-        p1[o] = o1; p2[o] = o2;
-        if (gl) { p1[o + M] = o1; p2[o + M] = o2; }
-        if (gr) { p1[o - M] = o1; p2[o - M] = o2; }
-        if (gb) {
-            p1[o + dyo] = o1; p2[o + dyo] = o2;
-            if (gl) { p1[o + dyo + M] = o1; p2[o + dyo + M] = o2; }
-            if (gr) { p1[o + dyo - M] = o1; p2[o + dyo - M] = o2; }
+        for (int t = 0; t < 8; ++t) {
+            const int k = lt + t * TPR;
+            if (k == 0 || k == half) {
+                v[t] = __ldg(in + k);
+            } else {
+                const double2 X = __ldg(in + k), Y = __ldg(in + N - k);
+                // k < N/2: X = U1[k], Y = U2[k] -> U1 + i U2
+                // k > N/2: X = U2[k'], Y = U1[k'] (k' = N-k) -> conj(U1) + i conj(U2)
+                v[t] = (k < half) ? make_double2(X.x - Y.y, X.y + Y.x) : make_double2(Y.x + X.y, X.x - Y.y);
+            }
         }
-        if (gt) {
-            p1[o - dyo] = o1; p2[o - dyo] = o2;
-            if (gl) { p1[o - dyo + M] = o1; p2[o - dyo + M] = o2; }
-            if (gr) { p1[o - dyo - M] = o1; p2[o - dyo - M] = o2; }
+        fft.template run<false>(v, s, lt);
+        if (live) {
+            const double gauge = a.use_gauge ? a.scal[member * 4 + 1] : 0.0;
+            double* __restrict__ p1 = a.psi1 + member * a.mstride;
+            double* __restrict__ p2 = a.psi2 + member * a.mstride;
+            const bool gb = row < GHOST, gt = row >= P - GHOST;
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                const int n = F::out_index(lt, e);
+                const double2 z = v[e];
+                const double t1 = z.x - gauge;            // pinned node: psi~1(0,0) = 0
+                const double o1 = A0 * t1 + A1 * z.y;     // src/model.jl:196
+                const double o2 = A2 * t1 + A3 * z.y;
+                const int64_t o = a.g.at(n, row);
+                const bool gl = n < GHOST, gr = n >= M - GHOST;
+                p1[o] = o1; p2[o] = o2;
+                if (gl) { p1[o + M] = o1; p2[o + M] = o2; }
+                if (gr) { p1[o - M] = o1; p2[o - M] = o2; }
+                if (gb) {
+                    p1[o + dyo] = o1; p2[o + dyo] = o2;
+                    if (gl) { p1[o + dyo + M] = o1; p2[o + dyo + M] = o2; }
+                    if (gr) { p1[o + dyo - M] = o1; p2[o + dyo - M] = o2; }
+                }
+                if (gt) {
+                    p1[o - dyo] = o1; p2[o - dyo] = o2;
+                    if (gl) { p1[o - dyo + M] = o1; p2[o - dyo + M] = o2; }
+                    if (gr) { p1[o - dyo - M] = o1; p2[o - dyo - M] = o2; }
+                }
+            }
         }
+        __syncthreads();
     }
 }
 
@@ -353,6 +438,62 @@ k4_dft_inverse(const FftArgs a) {
     }
 }
 
+// ---------------------------------------------------------------------------------------
+// launchers
+// ---------------------------------------------------------------------------------------
+static int g_num_sms = 0;
+static int num_sms() {
+    if (!g_num_sms) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
+        if (g_num_sms <= 0) g_num_sms = 148;
+    }
+    return g_num_sms;
+}
+
+template <int LOG2N, bool FWD>
+static cudaError_t launch_pow2(Handle* h, const FftArgs& a) {
+    using L = FftLaunch<LOG2N>;
+    auto kern = FWD ? k2_fft_forward<LOG2N> : k4_fft_inverse<LOG2N>;
+    static bool configured = false;
+    static int blocks_per_sm = 1;
+    if (!configured) {
+        if (L::SMEM > 48 * 1024) {
+            cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::SMEM);
+            if (e != cudaSuccess) return e;
+        }
+        cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, kern, L::THREADS, L::SMEM);
+        if (e != cudaSuccess) return e;
+        if (blocks_per_sm < 1) blocks_per_sm = 1;
+        configured = true;
+    }
+    const int gpm = (h->plan.P + L::RPB - 1) / L::RPB;
+    const int total = gpm * h->nm;
+    int grid = num_sms() * blocks_per_sm;
+    if (grid > total) grid = total;
+    kern<<<grid, L::THREADS, L::SMEM, h->stream>>>(a, gpm, total);
+    return cudaGetLastError();
+}
+
+template <bool FWD>
+static cudaError_t dispatch_pow2(Handle* h, const FftArgs& a) {
+    switch (h->plan.log2M) {
+        case 3: return launch_pow2<3, FWD>(h, a);
+        case 4: return launch_pow2<4, FWD>(h, a);
+        case 5: return launch_pow2<5, FWD>(h, a);
+        case 6: return launch_pow2<6, FWD>(h, a);
+        case 7: return launch_pow2<7, FWD>(h, a);
+        case 8: return launch_pow2<8, FWD>(h, a);
+        case 9: return launch_pow2<9, FWD>(h, a);
+        case 10: return launch_pow2<10, FWD>(h, a);
+        case 11: return launch_pow2<11, FWD>(h, a);
+        case 12: return launch_pow2<12, FWD>(h, a);
+        case 13: return launch_pow2<13, FWD>(h, a);
+        default: return cudaErrorInvalidValue;
+    }
+}
+
 static cudaError_t set_smem(const void* fn, size_t bytes) {
     if (bytes > 48 * 1024)
         return cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
@@ -371,19 +512,12 @@ cudaError_t launch_fft_forward(Handle* h, const double* q_fields, int /*which*/)
     for (int i = 0; i < 4; ++i) a.A[i] = h->prm.Pinv[i];
     a.scal = h->scal;
     KernelTimer t(h, QG_K_FFT_FWD);
-    if (h->plan.pow2) {
-        const size_t smem = (size_t)h->plan.rpb * h->plan.M * sizeof(double2);
-        cudaError_t e = set_smem((const void*)k2_fft_forward, smem);
-        if (e != cudaSuccess) return e;
-        dim3 grid((h->plan.P + h->plan.rpb - 1) / h->plan.rpb, h->nm);
-        k2_fft_forward<<<grid, h->plan.rpb * h->plan.tpr, smem, h->stream>>>(a);
-    } else {
-        const size_t smem = 2 * (size_t)h->plan.M * sizeof(double2);
-        cudaError_t e = set_smem((const void*)k2_dft_forward, smem);
-        if (e != cudaSuccess) return e;
-        dim3 grid(h->plan.P, h->nm);
-        k2_dft_forward<<<grid, 256, smem, h->stream>>>(a);
-    }
+    if (h->plan.pow2) return dispatch_pow2<true>(h, a);
+    const size_t smem = 2 * (size_t)h->plan.M * sizeof(double2);
+    cudaError_t e = set_smem((const void*)k2_dft_forward, smem);
+    if (e != cudaSuccess) return e;
+    dim3 grid(h->plan.P, h->nm);
+    k2_dft_forward<<<grid, 256, smem, h->stream>>>(a);
     return cudaGetLastError();
 }
 
@@ -400,19 +534,12 @@ cudaError_t launch_fft_inverse(Handle* h, double* psi_fields, int use_gauge) {
     a.scal = h->scal;
     a.use_gauge = use_gauge;
     KernelTimer t(h, QG_K_FFT_INV);
-    if (h->plan.pow2) {
-        const size_t smem = (size_t)h->plan.rpb * h->plan.M * sizeof(double2);
-        cudaError_t e = set_smem((const void*)k4_fft_inverse, smem);
-        if (e != cudaSuccess) return e;
-        dim3 grid((h->plan.P + h->plan.rpb - 1) / h->plan.rpb, h->nm);
-        k4_fft_inverse<<<grid, h->plan.rpb * h->plan.tpr, smem, h->stream>>>(a);
-    } else {
-        const size_t smem = 2 * (size_t)h->plan.M * sizeof(double2);
-        cudaError_t e = set_smem((const void*)k4_dft_inverse, smem);
-        if (e != cudaSuccess) return e;
-        dim3 grid(h->plan.P, h->nm);
-        k4_dft_inverse<<<grid, 256, smem, h->stream>>>(a);
-    }
+    if (h->plan.pow2) return dispatch_pow2<false>(h, a);
+    const size_t smem = 2 * (size_t)h->plan.M * sizeof(double2);
+    cudaError_t e = set_smem((const void*)k4_dft_inverse, smem);
+    if (e != cudaSuccess) return e;
+    dim3 grid(h->plan.P, h->nm);
+    k4_dft_inverse<<<grid, 256, smem, h->stream>>>(a);
     return cudaGetLastError();
 }
 

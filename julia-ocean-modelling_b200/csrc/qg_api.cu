@@ -348,8 +348,6 @@ int qg_create(const qg_params* p, int device, int nmembers, void* stream, qg_han
         QG_TRY(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
         h->own_stream = true;
     }
-    QG_TRY(cudaEventCreate(&h->ev0));
-    QG_TRY(cudaEventCreate(&h->ev1));
     const size_t fbytes = (size_t)h->nfields * h->g.fstride * sizeof(double);
     QG_TRY(cudaMalloc((void**)&h->q, fbytes));
     QG_TRY(cudaMalloc((void**)&h->psi, fbytes));
@@ -380,8 +378,7 @@ int qg_destroy(qg_handle* h) {
     free_plan(h);
     cudaFree(h->q); cudaFree(h->psi); cudaFree(h->f); cudaFree(h->S); cudaFree(h->k0sol);
     cudaFree(h->scal); cudaFree(h->stage); cudaFree(h->diag_part);
-    if (h->ev0) cudaEventDestroy(h->ev0);
-    if (h->ev1) cudaEventDestroy(h->ev1);
+    for (cudaEvent_t e : h->evpool) cudaEventDestroy(e);
     if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
     delete h;
     return QG_OK;
@@ -562,11 +559,20 @@ int qg_set_profiling(qg_handle* h, int enabled) {
     if (!h) return QG_ERR_INVALID;
     h->profiling = enabled ? 1 : 0;
     for (int i = 0; i < QG_NKERNELS; ++i) { h->kms[i] = 0.0; h->kcount[i] = 0; }
+    h->evkernel.clear();
     return QG_OK;
 }
 
 int qg_kernel_times(qg_handle* h, double* ms, int64_t* launches) {
     if (!h) return QG_ERR_INVALID;
+    QG_CUDA(h, cudaSetDevice(h->device));
+    QG_CUDA(h, cudaStreamSynchronize(h->stream));
+    for (size_t n = 0; n < h->evkernel.size(); ++n) {   // fold the recorded pairs into the sums
+        float t = 0.f;
+        QG_CUDA(h, cudaEventElapsedTime(&t, h->evpool[2 * n], h->evpool[2 * n + 1]));
+        h->kms[h->evkernel[n]] += t;
+    }
+    h->evkernel.clear();
     for (int i = 0; i < QG_NKERNELS; ++i) {
         if (ms) ms[i] = h->kms[i];
         if (launches) launches[i] = h->kcount[i];

@@ -136,7 +136,19 @@ struct Handle {
     int diag_blocks = 0;
     int64_t launches = 0;
     int profiling = 0;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    std::vector<cudaEvent_t> evpool;   // start/stop pairs
+    std::vector<int> evkernel;         // kernel id of each recorded pair
+    int ev_next(int id) {
+        const size_t n = evkernel.size();
+        if (2 * n + 2 > evpool.size()) {
+            cudaEvent_t a = nullptr, b = nullptr;
+            if (cudaEventCreate(&a) != cudaSuccess || cudaEventCreate(&b) != cudaSuccess) return -1;
+            evpool.push_back(a);
+            evpool.push_back(b);
+        }
+        evkernel.push_back(id);
+        return (int)n;
+    }
     double kms[QG_NKERNELS] = {0};
     int64_t kcount[QG_NKERNELS] = {0};
     std::string err;
@@ -147,23 +159,23 @@ struct Handle {
     int zindex(int slot, int member, int layer) const { return (slot * nm + member) * 2 + layer; }
 };
 
-// Wraps a kernel launch with optional CUDA-event timing on the handle's stream.
+// Wraps a kernel launch.  With profiling on, a start/stop CUDA-event pair is recorded around
+// the launch on the handle's stream (no host synchronisation: the events are read back in
+// qg_kernel_times), so per-kernel durations can be taken inside a timed region.
 struct KernelTimer {
     Handle* h;
     int id;
+    int slot = -1;
     KernelTimer(Handle* h_, int id_) : h(h_), id(id_) {
-        if (h->profiling) cudaEventRecord(h->ev0, h->stream);
+        if (h->profiling) {
+            slot = h->ev_next(id);
+            if (slot >= 0) cudaEventRecord(h->evpool[2 * slot], h->stream);
+        }
     }
     ~KernelTimer() {
         h->launches++;
         h->kcount[id]++;
-        if (h->profiling) {
-            cudaEventRecord(h->ev1, h->stream);
-            cudaEventSynchronize(h->ev1);
-            float ms = 0.f;
-            cudaEventElapsedTime(&ms, h->ev0, h->ev1);
-            h->kms[id] += ms;
-        }
+        if (slot >= 0) cudaEventRecord(h->evpool[2 * slot + 1], h->stream);
     }
 };
 

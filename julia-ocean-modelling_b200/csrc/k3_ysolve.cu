@@ -117,7 +117,7 @@ __global__ void __launch_bounds__(256) k3_gauge(const YArgs a) {
 
 // ---- the cluster kernel ------------------------------------------------------------------
 // grid = (slabs * CS, members), cluster = (CS,1,1), block = 32 * wpc threads.
-// dynamic smem: 4 arrays [wpc*m][32] (F, G, A, B) + 3 arrays [32] (FF, RR, GG).
+// dynamic smem: 4 arrays [wpc*m][32] (F, G, A, B) + 4 arrays [32] (FF, RR, X, Y).
 template <bool KEEP>
 __global__ void __launch_bounds__(512) k3_ysolve(const YArgs a) {
     extern __shared__ __align__(16) double ysm[];
@@ -185,61 +185,79 @@ __global__ void __launch_bounds__(512) k3_ysolve(const YArgs a) {
     auto rho_of = [&](int c) { return c < C - 1 ? rho32 : (c == C - 1 ? rhoL : 1.0); };
     auto h_of = [&](int c) { return c < C - 1 ? h32 : (c == C - 1 ? hL : 0.0); };
 
-    // ---- CTA-level forward aggregate ----------------------------------------------------
+    // ---- carries: one exchange round across the cluster ---------------------------------------
+    // Within the CTA the carry into local chunk lc is affine in the carry A_s into the CTA's
+    // first chunk:  A_lc = pF_lc + Rpre_lc * A_s.  The backward sums need the true forward
+    // values, G'_lc = G_lc + h_lc * A_lc, so the CTA's backward aggregate is affine in A_s too:
+    // GG' = X + Y * A_s.  Publishing (FF, RR, X, Y) lets every CTA close both cyclic
+    // recurrences after a single cluster.sync().
+    double* sX = sGG;          // [32]
+    double* sY = sGG + 32;     // [32]  (the launcher reserves 4 trailing rows)
     if (warp == 0) {
-        double t = 0.0, R = 1.0;
+        double t = 0.0, R = 1.0, X = 0.0, Y = 0.0;
+#pragma unroll 4
         for (int lc = 0; lc < nloc; ++lc) {
-            const double rho = rho_of(cta_c0 + lc);
-            t = fma(rho, t, sF[lc * 32 + lane]);
+            const int c = cta_c0 + lc;
+            const double rho = rho_of(c), hh = h_of(c);
+            const double F = sF[lc * 32 + lane], G = sG[lc * 32 + lane];
+            sA[lc * 32 + lane] = t;    // pF
+            sB[lc * 32 + lane] = R;    // Rpre
+            const double g0 = fma(hh, t, G), g1 = hh * R;
+            X = fma(R, g0, X);
+            Y = fma(R, g1, Y);
+            t = fma(rho, t, F);
             R *= rho;
         }
         sFF[lane] = t;
         sRR[lane] = R;
+        sX[lane] = X;
+        sY[lane] = Y;
     }
     cluster.sync();
 
-    // ---- forward carries, then the A-dependent backward sums ---------------------------------
     if (warp == 0) {
-        double t = 0.0, mine = 0.0;
-        // closure over the CS CTAs: y at the last row of the column
-        for (int i = 0; i < CS; ++i) {
-            const double* rFF = cluster.map_shared_rank(sFF, i);
-            const double* rRR = cluster.map_shared_rank(sRR, i);
-            t = fma(rRR[lane], t, rFF[lane]);
+        double FFi[8], RRi[8], Xi[8], Yi[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            if (i < CS) {
+                FFi[i] = cluster.map_shared_rank(sFF, i)[lane];
+                RRi[i] = cluster.map_shared_rank(sRR, i)[lane];
+                Xi[i] = cluster.map_shared_rank(sX, i)[lane];
+                Yi[i] = cluster.map_shared_rank(sY, i)[lane];
+            } else {
+                FFi[i] = 0.0; RRi[i] = 1.0; Xi[i] = 0.0; Yi[i] = 0.0;
+            }
         }
-        double acar = t * inv1;   // carry into chunk 0 (cyclic)
-        for (int i = 0; i < cr; ++i) {
-            const double* rFF = cluster.map_shared_rank(sFF, i);
-            const double* rRR = cluster.map_shared_rank(sRR, i);
-            acar = fma(rRR[lane], acar, rFF[lane]);
-        }
-        (void)mine;
-        double g = 0.0;
-        for (int lc = 0; lc < nloc; ++lc) {
-            const int c = cta_c0 + lc;
-            sA[lc * 32 + lane] = acar;
-            sG[lc * 32 + lane] = fma(acar, h_of(c), sG[lc * 32 + lane]);
-            acar = fma(rho_of(c), acar, sF[lc * 32 + lane]);
-        }
-        for (int lc = nloc - 1; lc >= 0; --lc) g = fma(rho_of(cta_c0 + lc), g, sG[lc * 32 + lane]);
-        sGG[lane] = g;
-    }
-    cluster.sync();
-
-    // ---- backward carries ------------------------------------------------------------------
-    if (warp == 0) {
         double t = 0.0;
-        for (int i = CS - 1; i >= 0; --i) {
-            const double* rGG = cluster.map_shared_rank(sGG, i);
-            const double* rRR = cluster.map_shared_rank(sRR, i);
-            t = fma(rRR[lane], t, rGG[lane]);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) t = fma(RRi[i], t, FFi[i]);
+        double As[8];
+        As[0] = t * inv1;   // carry into chunk 0 = y at the last row (cyclic closure)
+#pragma unroll
+        for (int i = 0; i < 7; ++i) As[i + 1] = fma(RRi[i], As[i], FFi[i]);
+        double GGp[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) GGp[i] = fma(Yi[i], As[i], Xi[i]);
+        t = 0.0;
+#pragma unroll
+        for (int i = 7; i >= 0; --i) t = fma(RRi[i], t, GGp[i]);
+        double Be[8];
+        Be[7] = t * inv1;   // carry into the last chunk = z at row 0 (cyclic closure)
+#pragma unroll
+        for (int i = 7; i > 0; --i) Be[i - 1] = fma(RRi[i], Be[i], GGp[i]);
+        double a_s = 0.0, b_e = 0.0;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            if (i == cr) { a_s = As[i]; b_e = Be[i]; }
         }
-        double bcar = t * inv1;   // carry into the last chunk (cyclic)
-        for (int i = CS - 1; i > cr; --i) {
-            const double* rGG = cluster.map_shared_rank(sGG, i);
-            const double* rRR = cluster.map_shared_rank(sRR, i);
-            bcar = fma(rRR[lane], bcar, rGG[lane]);
+#pragma unroll 4
+        for (int lc = 0; lc < nloc; ++lc) {
+            const double A = fma(sB[lc * 32 + lane], a_s, sA[lc * 32 + lane]);
+            sA[lc * 32 + lane] = A;
+            sG[lc * 32 + lane] = fma(A, h_of(cta_c0 + lc), sG[lc * 32 + lane]);
         }
+        double bcar = b_e;
+#pragma unroll 4
         for (int lc = nloc - 1; lc >= 0; --lc) {
             sB[lc * 32 + lane] = bcar;
             bcar = fma(rho_of(cta_c0 + lc), bcar, sG[lc * 32 + lane]);
@@ -300,6 +318,173 @@ __global__ void __launch_bounds__(512) k3_ysolve(const YArgs a) {
     cluster.sync();   // keep distributed shared memory alive until every CTA has read it
 }
 
+// ---- TMA-staged variant ---------------------------------------------------------------------
+// Same algorithm, different residency: the CTA's part of the slab (rows_cta rows x 16 columns,
+// one 128-byte line per row) is brought into shared memory by TMA tensor copies
+// (cp.async.bulk.tensor.2d, one 32-row box per chunk, all completing on one mbarrier) and the
+// sweeps run out of shared memory with a handful of registers, so several CTAs of different
+// clusters share an SM and their load / compute / store phases overlap.  A half-warp owns a
+// chunk (16 lanes = 16 adjacent columns); pass 2 stores straight to global memory.
+// grid = (slabs * CS, members), cluster = (CS,1,1), block = 16 * nchunk threads.
+constexpr int TS_WC = 16;
+
+__global__ void __launch_bounds__(256, 3)
+k3_ysolve_tma(const __grid_constant__ CUtensorMap tmS, const YArgs a, int nchunk) {
+    extern __shared__ __align__(128) unsigned char ts_raw[];
+    cg::cluster_group cluster = cg::this_cluster();
+    const int CS = (int)cluster.num_blocks();
+    const int cr = (int)cluster.block_rank();
+    const int C = a.pl.C, P = a.pl.P, ncol = a.pl.ncol;
+    const int tid = threadIdx.x;
+    const int chunk = tid >> 4, l = tid & 15;
+    const int slab = blockIdx.x / CS;
+    const int member = blockIdx.y;
+    const int col0 = slab * TS_WC;
+    const int col = col0 + l;
+    const bool cvalid = col < ncol;
+    const int ccol = cvalid ? col : 0;
+
+    double* tile = reinterpret_cast<double*>(ts_raw);                  // [nchunk*32][16]
+    double* pw = tile + (size_t)nchunk * 32 * TS_WC;                   // [32][16]  r^(i+1)
+    double* sF = pw + 32 * TS_WC;                                      // [nchunk][16]
+    double* sG = sF + nchunk * TS_WC;
+    double* sA = sG + nchunk * TS_WC;
+    double* sB = sA + nchunk * TS_WC;
+    double* sFF = sB + nchunk * TS_WC;                                 // [16] each
+    double* sRR = sFF + TS_WC;
+    double* sX = sRR + TS_WC;
+    double* sY = sX + TS_WC;
+    uint64_t* bar = reinterpret_cast<uint64_t*>(sY + TS_WC);
+
+    const int c0 = cr * nchunk;                 // first global chunk of this CTA
+    const int nact = max(0, min(nchunk, C - c0));   // chunks that hold rows
+    if (tid == 0) mbar_init(bar, 1);
+    __syncthreads();
+    if (tid == 0 && nact > 0) {
+        mbar_expect_tx(bar, (uint32_t)nact * 32 * TS_WC * sizeof(double));
+        for (int k = 0; k < nact; ++k)
+            tma_load_2d(tile + (size_t)k * 32 * TS_WC, &tmS, col0, member * P + (c0 + k) * 32, bar);
+    }
+    const double r = cvalid ? __ldg(a.pl.rtab + ccol) : 0.0;
+    const double kap = cvalid ? __ldg(a.pl.kap + ccol) : 0.0;
+    const double pinv = (a.pinned && cvalid) ? __ldg(a.pl.pinw + ccol) * a.scal[member * 4 + 0] : 0.0;
+    if (chunk == 0) {
+        double p = r;
+        for (int i = 0; i < 32; ++i) {
+            pw[i * TS_WC + l] = p;
+            p *= r;
+        }
+    }
+    const int c = c0 + chunk;
+    const int j0 = c * 32;
+    const int len = c < C ? min(32, P - j0) : 0;
+    double* t = tile + (size_t)chunk * 32 * TS_WC + l;
+    if (nact > 0) mbar_wait(bar, 0);
+
+    // ---- pass 1: zero-carry forward recurrence in place, forward end value and backward sum ----
+    {
+        double y = 0.0, G = 0.0, p = 1.0;
+        for (int i = 0; i < len; ++i) {
+            double b = t[i * TS_WC];
+            if (j0 + i == 0) b -= pinv;
+            y = fma(r, y, b);
+            t[i * TS_WC] = y;
+            G = fma(p, y, G);
+            p *= r;
+        }
+        sF[chunk * TS_WC + l] = y;
+        sG[chunk * TS_WC + l] = G;
+    }
+    __syncthreads();
+
+    // ---- carries (see k3_ysolve): one exchange round across the cluster ---------------------
+    const double rho32 = cvalid ? __ldg(a.pl.rho32 + ccol) : 0.0;
+    const double rhoL = cvalid ? __ldg(a.pl.rhoL + ccol) : 0.0;
+    const double h32 = cvalid ? __ldg(a.pl.h32 + ccol) : 0.0;
+    const double hL = cvalid ? __ldg(a.pl.hL + ccol) : 0.0;
+    const double inv1 = cvalid ? __ldg(a.pl.inv1mrP + ccol) : 0.0;
+    auto rho_of = [&](int cc) { return cc < C - 1 ? rho32 : (cc == C - 1 ? rhoL : 1.0); };
+    auto h_of = [&](int cc) { return cc < C - 1 ? h32 : (cc == C - 1 ? hL : 0.0); };
+    if (tid < TS_WC) {
+        double tt = 0.0, R = 1.0, X = 0.0, Y = 0.0;
+        for (int lc = 0; lc < nchunk; ++lc) {
+            const double rho = rho_of(c0 + lc), hh = h_of(c0 + lc);
+            const double F = sF[lc * TS_WC + l], G = sG[lc * TS_WC + l];
+            sA[lc * TS_WC + l] = tt;   // pF
+            sB[lc * TS_WC + l] = R;    // Rpre
+            const double g0 = fma(hh, tt, G), g1 = hh * R;
+            X = fma(R, g0, X);
+            Y = fma(R, g1, Y);
+            tt = fma(rho, tt, F);
+            R *= rho;
+        }
+        sFF[l] = tt; sRR[l] = R; sX[l] = X; sY[l] = Y;
+    }
+    cluster.sync();
+    if (tid < TS_WC) {
+        double FFi[8], RRi[8], Xi[8], Yi[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            if (i < CS) {
+                FFi[i] = cluster.map_shared_rank(sFF, i)[l];
+                RRi[i] = cluster.map_shared_rank(sRR, i)[l];
+                Xi[i] = cluster.map_shared_rank(sX, i)[l];
+                Yi[i] = cluster.map_shared_rank(sY, i)[l];
+            } else {
+                FFi[i] = 0.0; RRi[i] = 1.0; Xi[i] = 0.0; Yi[i] = 0.0;
+            }
+        }
+        double tt = 0.0;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) tt = fma(RRi[i], tt, FFi[i]);
+        double As[8];
+        As[0] = tt * inv1;
+#pragma unroll
+        for (int i = 0; i < 7; ++i) As[i + 1] = fma(RRi[i], As[i], FFi[i]);
+        double GGp[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) GGp[i] = fma(Yi[i], As[i], Xi[i]);
+        tt = 0.0;
+#pragma unroll
+        for (int i = 7; i >= 0; --i) tt = fma(RRi[i], tt, GGp[i]);
+        double Be[8];
+        Be[7] = tt * inv1;
+#pragma unroll
+        for (int i = 7; i > 0; --i) Be[i - 1] = fma(RRi[i], Be[i], GGp[i]);
+        double a_s = 0.0, b_e = 0.0;
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+            if (i == cr) { a_s = As[i]; b_e = Be[i]; }
+        for (int lc = 0; lc < nchunk; ++lc) {
+            const double A = fma(sB[lc * TS_WC + l], a_s, sA[lc * TS_WC + l]);
+            sA[lc * TS_WC + l] = A;
+            sG[lc * TS_WC + l] = fma(A, h_of(c0 + lc), sG[lc * TS_WC + l]);
+        }
+        double bcar = b_e;
+        for (int lc = nchunk - 1; lc >= 0; --lc) {
+            sB[lc * TS_WC + l] = bcar;
+            bcar = fma(rho_of(c0 + lc), bcar, sG[lc * TS_WC + l]);
+        }
+    }
+    __syncthreads();
+
+    // ---- pass 2: add the carry, backward recurrence, scale, store --------------------------------
+    {
+        const double A = sA[chunk * TS_WC + l], B = sB[chunk * TS_WC + l];
+        const double* __restrict__ k0 = a.k0sol + (int64_t)member * P;
+        double* __restrict__ out = a.S + member * a.sstride + (int64_t)j0 * ncol + ccol;
+        double z = B;
+        for (int i = len - 1; i >= 0; --i) {
+            const double y = fma(pw[i * TS_WC + l], A, t[i * TS_WC]);
+            z = fma(r, z, y);
+            double v = kap * z;
+            if (col == 0) v = k0[j0 + i];
+            if (cvalid) out[(int64_t)i * ncol] = v;
+        }
+    }
+    cluster.sync();   // distributed shared memory must outlive every remote read
+}
+
 cudaError_t launch_ysolve(Handle* h, int pinned, int /*unused*/) {
     YArgs a{};
     a.pl = h->plan;
@@ -314,13 +499,38 @@ cudaError_t launch_ysolve(Handle* h, int pinned, int /*unused*/) {
     }
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
-    {
+    if (h->plan.ts_ok) {
+        const Plan& pl = h->plan;
+        const int nslab = (pl.ncol + TS_WC - 1) / TS_WC;
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = dim3(nslab * pl.ts_CS, h->nm, 1);
+        cfg.blockDim = dim3(16 * pl.ts_nchunk, 1, 1);
+        cfg.dynamicSmemBytes = ((size_t)pl.ts_nchunk * 32 * TS_WC + 32 * TS_WC + 4 * pl.ts_nchunk * TS_WC +
+                                4 * TS_WC) * sizeof(double) + 16;
+        cfg.stream = h->stream;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = pl.ts_CS;
+        attr[0].val.clusterDim.y = 1;
+        attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        static size_t configured = 0;
+        if (cfg.dynamicSmemBytes > configured) {
+            e = cudaFuncSetAttribute(k3_ysolve_tma, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)cfg.dynamicSmemBytes);
+            if (e != cudaSuccess) return e;
+            configured = cfg.dynamicSmemBytes;
+        }
+        KernelTimer t(h, QG_K_YSOLVE);
+        e = cudaLaunchKernelEx(&cfg, k3_ysolve_tma, h->tm_S, a, pl.ts_nchunk);
+    } else {
         const Plan& pl = h->plan;
         const int nslab = (pl.ncol + 31) / 32;
         cudaLaunchConfig_t cfg{};
         cfg.gridDim = dim3(nslab * pl.CS, h->nm, 1);
         cfg.blockDim = dim3(32 * pl.wpc, 1, 1);
-        cfg.dynamicSmemBytes = (size_t)(4 * pl.wpc * pl.m + 3) * 32 * sizeof(double);
+        cfg.dynamicSmemBytes = (size_t)(4 * pl.wpc * pl.m + 4) * 32 * sizeof(double);
         cfg.stream = h->stream;
         cudaLaunchAttribute attr[1];
         attr[0].id = cudaLaunchAttributeClusterDimension;

@@ -171,6 +171,13 @@ cudaError_t build_plan(Handle* h) {
         pl.m = (pl.C + cs * pl.wpc - 1) / (cs * pl.wpc);
     }
     pl.k0scale = h->prm.dx * h->prm.dx / M;
+    {   // TMA-staged y-solve: at most 16 chunks (512 rows, 64 KB) per CTA, cluster of <= 8
+        int cs = 1;
+        while (cs < 8 && (pl.C + cs - 1) / cs > 16) cs *= 2;
+        pl.ts_CS = cs;
+        pl.ts_nchunk = (pl.C + cs - 1) / cs;
+        pl.ts_ok = (pl.ts_nchunk <= 16 && (pl.ncol % 16) == 0) ? 1 : 0;
+    }
 
     std::vector<double2> tw(M);
     for (int n = 0; n < M; ++n) {
@@ -251,6 +258,28 @@ static int make_tensor_map(Handle* h, CUtensorMap* tm, double* base) {
     if (r != CUDA_SUCCESS) {
         char b[128];
         snprintf(b, sizeof(b), "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+        return fail(h, QG_ERR_CUDA, b);
+    }
+    return QG_OK;
+}
+
+static int make_tensor_map_S(Handle* h) {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+    if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || !fn)
+        return fail(h, QG_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+    auto encode = (PFN_cuTensorMapEncodeTiled_v12000)fn;
+    const cuuint64_t dims[2] = {(cuuint64_t)h->plan.ncol, (cuuint64_t)h->plan.P * h->nm};
+    const cuuint64_t strides[1] = {(cuuint64_t)h->plan.ncol * sizeof(double)};
+    const cuuint32_t box[2] = {16, 32};   // TS_WC columns x one chunk (k3_ysolve.cu)
+    const cuuint32_t estr[2] = {1, 1};
+    CUresult r = encode(&h->tm_S, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, h->S, dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                        CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        char b[128];
+        snprintf(b, sizeof(b), "cuTensorMapEncodeTiled (spectral) failed with CUresult %d", (int)r);
         return fail(h, QG_ERR_CUDA, b);
     }
     return QG_OK;
@@ -364,6 +393,7 @@ int qg_create(const qg_params* p, int device, int nmembers, void* stream, qg_han
     QG_TRY(build_plan(h));
     rc = make_tensor_map(h, &h->tm_q, h->q);
     if (rc == QG_OK) rc = make_tensor_map(h, &h->tm_psi, h->psi);
+    if (rc == QG_OK && h->plan.ts_ok) rc = make_tensor_map_S(h);
     if (rc != QG_OK) return bail(rc);
     QG_TRY(cudaStreamSynchronize(h->stream));
 #undef QG_TRY

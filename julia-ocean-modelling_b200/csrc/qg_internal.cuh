@@ -67,7 +67,8 @@ struct Plan {
     int tpr, rpb;            // threads per row, rows per block (pow2 path)
     int C;                   // 32-row chunks in y
     int lenLast;             // rows in the last chunk
-    int wpc, CS, m;          // warps per CTA, cluster size, chunks per warp
+    int wpc, CS, m;          // warps per CTA, cluster size, chunks per warp (register variant)
+    int ts_ok, ts_CS, ts_nchunk;   // TMA-staged variant: usable, cluster size, chunks per CTA
     double2* tw;             // exp(-2 pi i n / M), n < M
     double *rtab, *kap, *rho32, *h32, *rhoL, *hL, *inv1mrP, *pinw;   // per real column
     double k0scale;          // dx^2 / M
@@ -125,7 +126,7 @@ struct Handle {
     int qcur = 0;                    // slot of the newest level of q and f_store
     int pcur = 0;                    // slot of the newest level of psi
     bool have_state = false;
-    CUtensorMap tm_q, tm_psi;
+    CUtensorMap tm_q, tm_psi, tm_S;
     Plan plan;
     bool plan_ok = false;
     double* S = nullptr;             // spectral scratch [nm][P][2M]
@@ -180,6 +181,54 @@ struct KernelTimer {
 };
 
 #ifdef __CUDACC__
+// ---- mbarrier / TMA primitives (inline PTX) ---------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+    return (uint32_t)__cvta_generic_to_shared(p);
+}
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)),
+                 "r"(bytes)
+                 : "memory");
+}
+
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* tm, int c0, int c1, int c2,
+                                            uint64_t* bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, "
+        "%4, %5}], [%2];" ::"r"(smem_u32(dst)),
+        "l"(tm), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+}
+
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* tm, int c0, int c1, uint64_t* bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, "
+        "%4}], [%2];" ::"r"(smem_u32(dst)),
+        "l"(tm), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+        : "memory");
+}
+
 // ---- block-wide helpers (blockDim.x == 1024) -----------------------------------------
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll

@@ -3,6 +3,7 @@
 #include <cudaTypedefs.h>
 #include <math.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <mutex>
@@ -237,7 +238,7 @@ void free_plan(Handle* h) {
     h->plan_ok = false;
 }
 
-static int make_tensor_map(Handle* h, CUtensorMap* tm, double* base) {
+static int make_tensor_map(Handle* h, CUtensorMap* tm, double* base, int bx, int by) {
     static PFN_cuTensorMapEncodeTiled_v12000 encode = nullptr;
     if (!encode) {
         void* fn = nullptr;
@@ -250,7 +251,7 @@ static int make_tensor_map(Handle* h, CUtensorMap* tm, double* base) {
     const cuuint64_t dims[3] = {(cuuint64_t)h->g.pitch, (cuuint64_t)h->g.rows, (cuuint64_t)h->nfields};
     const cuuint64_t strides[2] = {(cuuint64_t)h->g.pitch * sizeof(double),
                                    (cuuint64_t)h->g.fstride * sizeof(double)};
-    const cuuint32_t box[3] = {K1_BX, K1_BY, 1};
+    const cuuint32_t box[3] = {(cuuint32_t)bx, (cuuint32_t)by, 1};
     const cuuint32_t estr[3] = {1, 1, 1};
     CUresult r = encode(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, base, dims, strides, box, estr,
                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
@@ -391,8 +392,13 @@ int qg_create(const qg_params* p, int device, int nmembers, void* stream, qg_han
     h->diag_blocks = p->P < 592 ? p->P : 592;
     QG_TRY(cudaMalloc((void**)&h->diag_part, ((size_t)nmembers * h->diag_blocks * 2 + 2 * nmembers) * sizeof(double)));
     QG_TRY(build_plan(h));
-    rc = make_tensor_map(h, &h->tm_q, h->q);
-    if (rc == QG_OK) rc = make_tensor_map(h, &h->tm_psi, h->psi);
+    {
+        const char* ty = getenv("QG_K1_TY");
+        const int v = ty ? atoi(ty) : (p->P >= 512 ? 24 : 16);   // measured on B200: 24 rows is best at 4096^2
+        h->k1_ty = (v == 8 || v == 12 || v == 24) ? v : 16;
+    }
+    rc = make_tensor_map(h, &h->tm_q, h->q, K1_TX + 2 * GHOST, h->k1_ty + 2);
+    if (rc == QG_OK) rc = make_tensor_map(h, &h->tm_psi, h->psi, K1_TX + 2 * GHOST, h->k1_ty + 2 * GHOST);
     if (rc == QG_OK && h->plan.ts_ok) rc = make_tensor_map_S(h);
     if (rc != QG_OK) return bail(rc);
     QG_TRY(cudaStreamSynchronize(h->stream));

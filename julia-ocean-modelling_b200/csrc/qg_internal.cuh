@@ -24,9 +24,7 @@ constexpr int GHOST = 2;
 
 // K1 tile geometry (k1_zeta.cu); the TMA box is (K1_BX, K1_BY, 1).
 constexpr int K1_TX = 128;
-constexpr int K1_TY = 16;
-constexpr int K1_BX = K1_TX + 2 * GHOST;   // 132 doubles = 1056 B (multiple of 16 B)
-constexpr int K1_BY = K1_TY + 2 * GHOST;   // 20
+constexpr int K1_THREADS = 256;
 
 struct Geom {
     int M, P;
@@ -127,6 +125,7 @@ struct Handle {
     int pcur = 0;                    // slot of the newest level of psi
     bool have_state = false;
     CUtensorMap tm_q, tm_psi, tm_S;
+    int k1_ty = 16;                  // K1 tile height (8, 12, 16 or 24; env QG_K1_TY)
     Plan plan;
     bool plan_ok = false;
     double* S = nullptr;             // spectral scratch [nm][P][2M]

@@ -327,6 +327,7 @@ __global__ void __launch_bounds__(512) k3_ysolve(const YArgs a) {
 // chunk (16 lanes = 16 adjacent columns); pass 2 stores straight to global memory.
 // grid = (slabs * CS, members), cluster = (CS,1,1), block = 16 * nchunk threads.
 constexpr int TS_WC = 16;
+constexpr int TS_LD = 17;   // padded leading dimension of the per-chunk carry arrays
 
 __global__ void __launch_bounds__(256, 3)
 k3_ysolve_tma(const __grid_constant__ CUtensorMap tmS, const YArgs a, int nchunk) {
@@ -346,11 +347,9 @@ k3_ysolve_tma(const __grid_constant__ CUtensorMap tmS, const YArgs a, int nchunk
 
     double* tile = reinterpret_cast<double*>(ts_raw);                  // [nchunk*32][16]
     double* pw = tile + (size_t)nchunk * 32 * TS_WC;                   // [32][16]  r^(i+1)
-    double* sF = pw + 32 * TS_WC;                                      // [nchunk][16]
-    double* sG = sF + nchunk * TS_WC;
-    double* sA = sG + nchunk * TS_WC;
-    double* sB = sA + nchunk * TS_WC;
-    double* sFF = sB + nchunk * TS_WC;                                 // [16] each
+    double* sF = pw + 32 * TS_WC;                                      // [nchunk][TS_LD]
+    double* sG = sF + nchunk * TS_LD;
+    double* sFF = sG + nchunk * TS_LD;                                 // [16] each
     double* sRR = sFF + TS_WC;
     double* sX = sRR + TS_WC;
     double* sY = sX + TS_WC;
@@ -368,7 +367,7 @@ k3_ysolve_tma(const __grid_constant__ CUtensorMap tmS, const YArgs a, int nchunk
     const double r = cvalid ? __ldg(a.pl.rtab + ccol) : 0.0;
     const double kap = cvalid ? __ldg(a.pl.kap + ccol) : 0.0;
     const double pinv = (a.pinned && cvalid) ? __ldg(a.pl.pinw + ccol) * a.scal[member * 4 + 0] : 0.0;
-    if (chunk == 0) {
+    if (chunk == 0) {   // first half-warp: powers r^(i+1) of this slab's columns
         double p = r;
         for (int i = 0; i < 32; ++i) {
             pw[i * TS_WC + l] = p;
@@ -377,13 +376,15 @@ k3_ysolve_tma(const __grid_constant__ CUtensorMap tmS, const YArgs a, int nchunk
     }
     const int c = c0 + chunk;
     const int j0 = c * 32;
-    const int len = c < C ? min(32, P - j0) : 0;
-    double* t = tile + (size_t)chunk * 32 * TS_WC + l;
+    const bool mine = chunk < nchunk;   // the block is padded to whole warps
+    const int len = (mine && c < C) ? min(32, P - j0) : 0;
+    double* t = tile + (size_t)(mine ? chunk : 0) * 32 * TS_WC + l;
     if (nact > 0) mbar_wait(bar, 0);
 
     // ---- pass 1: zero-carry forward recurrence in place, forward end value and backward sum ----
     {
         double y = 0.0, G = 0.0, p = 1.0;
+#pragma unroll 4
         for (int i = 0; i < len; ++i) {
             double b = t[i * TS_WC];
             if (j0 + i == 0) b -= pinv;
@@ -392,88 +393,124 @@ k3_ysolve_tma(const __grid_constant__ CUtensorMap tmS, const YArgs a, int nchunk
             G = fma(p, y, G);
             p *= r;
         }
-        sF[chunk * TS_WC + l] = y;
-        sG[chunk * TS_WC + l] = G;
+        if (mine) {
+            sF[chunk * TS_LD + l] = y;
+            sG[chunk * TS_LD + l] = G;
+        }
     }
     __syncthreads();
 
     // ---- carries (see k3_ysolve): one exchange round across the cluster ---------------------
-    const double rho32 = cvalid ? __ldg(a.pl.rho32 + ccol) : 0.0;
-    const double rhoL = cvalid ? __ldg(a.pl.rhoL + ccol) : 0.0;
-    const double h32 = cvalid ? __ldg(a.pl.h32 + ccol) : 0.0;
-    const double hL = cvalid ? __ldg(a.pl.hL + ccol) : 0.0;
-    const double inv1 = cvalid ? __ldg(a.pl.inv1mrP + ccol) : 0.0;
-    auto rho_of = [&](int cc) { return cc < C - 1 ? rho32 : (cc == C - 1 ? rhoL : 1.0); };
-    auto h_of = [&](int cc) { return cc < C - 1 ? h32 : (cc == C - 1 ? hL : 0.0); };
-    if (tid < TS_WC) {
-        double tt = 0.0, R = 1.0, X = 0.0, Y = 0.0;
-        for (int lc = 0; lc < nchunk; ++lc) {
-            const double rho = rho_of(c0 + lc), hh = h_of(c0 + lc);
-            const double F = sF[lc * TS_WC + l], G = sG[lc * TS_WC + l];
-            sA[lc * TS_WC + l] = tt;   // pF
-            sB[lc * TS_WC + l] = R;    // Rpre
-            const double g0 = fma(hh, tt, G), g1 = hh * R;
-            X = fma(R, g0, X);
-            Y = fma(R, g1, Y);
-            tt = fma(rho, tt, F);
-            R *= rho;
+    // Warp-level parallel cyclic reduction: lanes 0-15 / 16-31 of a warp hold the (up to 16) chunks
+    // of two columns; the affine maps x -> rho x + F compose by Kogge-Stone shuffles.
+    const int warp = tid >> 5, lane = tid & 31, nwarp = (blockDim.x + 31) >> 5;
+    const int slot = lane & 15, csel = lane >> 4;
+    const bool act = slot < nchunk;
+    const int cc = c0 + slot;
+    // forward scan of one column pair: returns the exclusive prefix (pF, Rpre) and the totals
+    auto fwd_scan = [&](double rho, double F, double& pF, double& Rpre, double& FFv, double& RRv) {
+        double R = rho, t = F;
+#pragma unroll
+        for (int d = 1; d < 16; d <<= 1) {
+            const double Rp = __shfl_up_sync(0xffffffffu, R, d, 16);
+            const double tp = __shfl_up_sync(0xffffffffu, t, d, 16);
+            if (slot >= d) {
+                t = fma(R, tp, t);
+                R *= Rp;
+            }
         }
-        sFF[l] = tt; sRR[l] = R; sX[l] = X; sY[l] = Y;
+        FFv = __shfl_sync(0xffffffffu, t, 15, 16);
+        RRv = __shfl_sync(0xffffffffu, R, 15, 16);
+        Rpre = __shfl_up_sync(0xffffffffu, R, 1, 16);
+        pF = __shfl_up_sync(0xffffffffu, t, 1, 16);
+        if (slot == 0) { Rpre = 1.0; pF = 0.0; }
+    };
+    for (int cb = warp; cb < TS_WC / 2; cb += nwarp) {
+        const int cl = 2 * cb + csel;                 // column within the slab
+        const int gc = (col0 + cl < ncol) ? col0 + cl : 0;
+        const double rho = !act || cc > C - 1 ? 1.0 : __ldg((cc == C - 1 ? a.pl.rhoL : a.pl.rho32) + gc);
+        const double hh = !act || cc > C - 1 ? 0.0 : __ldg((cc == C - 1 ? a.pl.hL : a.pl.h32) + gc);
+        const double F = act ? sF[slot * TS_LD + cl] : 0.0;
+        const double G = act ? sG[slot * TS_LD + cl] : 0.0;
+        double pF, Rpre, FFv, RRv;
+        fwd_scan(rho, F, pF, Rpre, FFv, RRv);
+        double Xv = Rpre * fma(hh, pF, G), Yv = Rpre * (hh * Rpre);
+#pragma unroll
+        for (int d = 8; d > 0; d >>= 1) {
+            Xv += __shfl_xor_sync(0xffffffffu, Xv, d, 16);
+            Yv += __shfl_xor_sync(0xffffffffu, Yv, d, 16);
+        }
+        if (slot == 0) { sFF[cl] = FFv; sRR[cl] = RRv; sX[cl] = Xv; sY[cl] = Yv; }
     }
     cluster.sync();
-    if (tid < TS_WC) {
-        double FFi[8], RRi[8], Xi[8], Yi[8];
+    for (int cb = warp; cb < TS_WC / 2; cb += nwarp) {
+        const int cl = 2 * cb + csel;
+        const int gc = (col0 + cl < ncol) ? col0 + cl : 0;
+        const double inv1 = __ldg(a.pl.inv1mrP + gc);
+        double FFi[8], RRi[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-            if (i < CS) {
-                FFi[i] = cluster.map_shared_rank(sFF, i)[l];
-                RRi[i] = cluster.map_shared_rank(sRR, i)[l];
-                Xi[i] = cluster.map_shared_rank(sX, i)[l];
-                Yi[i] = cluster.map_shared_rank(sY, i)[l];
-            } else {
-                FFi[i] = 0.0; RRi[i] = 1.0; Xi[i] = 0.0; Yi[i] = 0.0;
-            }
+            FFi[i] = i < CS ? cluster.map_shared_rank(sFF, i)[cl] : 0.0;
+            RRi[i] = i < CS ? cluster.map_shared_rank(sRR, i)[cl] : 1.0;
         }
         double tt = 0.0;
 #pragma unroll
         for (int i = 0; i < 8; ++i) tt = fma(RRi[i], tt, FFi[i]);
-        double As[8];
-        As[0] = tt * inv1;
-#pragma unroll
-        for (int i = 0; i < 7; ++i) As[i + 1] = fma(RRi[i], As[i], FFi[i]);
+        double as = tt * inv1;   // carry into chunk 0 = y at the last row (cyclic closure)
+        double a_s = 0.0;
         double GGp[8];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) GGp[i] = fma(Yi[i], As[i], Xi[i]);
+        for (int i = 0; i < 8; ++i) {
+            const double Xi = i < CS ? cluster.map_shared_rank(sX, i)[cl] : 0.0;
+            const double Yi = i < CS ? cluster.map_shared_rank(sY, i)[cl] : 0.0;
+            GGp[i] = fma(Yi, as, Xi);
+            if (i == cr) a_s = as;
+            as = fma(RRi[i], as, FFi[i]);
+        }
         tt = 0.0;
 #pragma unroll
         for (int i = 7; i >= 0; --i) tt = fma(RRi[i], tt, GGp[i]);
-        double Be[8];
-        Be[7] = tt * inv1;
+        double b_e = tt * inv1;   // carry into the last chunk = z at row 0 (cyclic closure)
 #pragma unroll
-        for (int i = 7; i > 0; --i) Be[i - 1] = fma(RRi[i], Be[i], GGp[i]);
-        double a_s = 0.0, b_e = 0.0;
+        for (int i = 7; i > 0; --i)
+            if (i > cr) b_e = fma(RRi[i], b_e, GGp[i]);
+
+        const double rho = !act || cc > C - 1 ? 1.0 : __ldg((cc == C - 1 ? a.pl.rhoL : a.pl.rho32) + gc);
+        const double hh = !act || cc > C - 1 ? 0.0 : __ldg((cc == C - 1 ? a.pl.hL : a.pl.h32) + gc);
+        const double F = act ? sF[slot * TS_LD + cl] : 0.0;
+        const double G = act ? sG[slot * TS_LD + cl] : 0.0;
+        double pF, Rpre, FFv, RRv;
+        fwd_scan(rho, F, pF, Rpre, FFv, RRv);
+        const double A = fma(Rpre, a_s, pF);
+        const double Gp = fma(A, hh, G);
+        // inclusive backward (suffix) scan of x -> rho x + G'
+        double R = rho, t = Gp;
 #pragma unroll
-        for (int i = 0; i < 8; ++i)
-            if (i == cr) { a_s = As[i]; b_e = Be[i]; }
-        for (int lc = 0; lc < nchunk; ++lc) {
-            const double A = fma(sB[lc * TS_WC + l], a_s, sA[lc * TS_WC + l]);
-            sA[lc * TS_WC + l] = A;
-            sG[lc * TS_WC + l] = fma(A, h_of(c0 + lc), sG[lc * TS_WC + l]);
+        for (int d = 1; d < 16; d <<= 1) {
+            const double Rp = __shfl_down_sync(0xffffffffu, R, d, 16);
+            const double tp = __shfl_down_sync(0xffffffffu, t, d, 16);
+            if (slot + d < 16) {
+                t = fma(R, tp, t);
+                R *= Rp;
+            }
         }
-        double bcar = b_e;
-        for (int lc = nchunk - 1; lc >= 0; --lc) {
-            sB[lc * TS_WC + l] = bcar;
-            bcar = fma(rho_of(c0 + lc), bcar, sG[lc * TS_WC + l]);
+        double Rex = __shfl_down_sync(0xffffffffu, R, 1, 16), tex = __shfl_down_sync(0xffffffffu, t, 1, 16);
+        if (slot == 15) { Rex = 1.0; tex = 0.0; }
+        if (act) {
+            sF[slot * TS_LD + cl] = A;                       // A overwrites F, B overwrites G
+            sG[slot * TS_LD + cl] = fma(Rex, b_e, tex);
         }
     }
+    cluster.barrier_arrive();   // remote reads are done; matched by barrier_wait() before exit
     __syncthreads();
 
     // ---- pass 2: add the carry, backward recurrence, scale, store --------------------------------
     {
-        const double A = sA[chunk * TS_WC + l], B = sB[chunk * TS_WC + l];
+        const double A = mine ? sF[chunk * TS_LD + l] : 0.0, B = mine ? sG[chunk * TS_LD + l] : 0.0;
         const double* __restrict__ k0 = a.k0sol + (int64_t)member * P;
         double* __restrict__ out = a.S + member * a.sstride + (int64_t)j0 * ncol + ccol;
         double z = B;
+#pragma unroll 4
         for (int i = len - 1; i >= 0; --i) {
             const double y = fma(pw[i * TS_WC + l], A, t[i * TS_WC]);
             z = fma(r, z, y);
@@ -482,7 +519,7 @@ k3_ysolve_tma(const __grid_constant__ CUtensorMap tmS, const YArgs a, int nchunk
             if (cvalid) out[(int64_t)i * ncol] = v;
         }
     }
-    cluster.sync();   // distributed shared memory must outlive every remote read
+    cluster.barrier_wait();   // distributed shared memory must outlive every remote read
 }
 
 cudaError_t launch_ysolve(Handle* h, int pinned, int /*unused*/) {
@@ -504,8 +541,8 @@ cudaError_t launch_ysolve(Handle* h, int pinned, int /*unused*/) {
         const int nslab = (pl.ncol + TS_WC - 1) / TS_WC;
         cudaLaunchConfig_t cfg{};
         cfg.gridDim = dim3(nslab * pl.ts_CS, h->nm, 1);
-        cfg.blockDim = dim3(16 * pl.ts_nchunk, 1, 1);
-        cfg.dynamicSmemBytes = ((size_t)pl.ts_nchunk * 32 * TS_WC + 32 * TS_WC + 4 * pl.ts_nchunk * TS_WC +
+        cfg.blockDim = dim3(((16 * pl.ts_nchunk + 31) / 32) * 32, 1, 1);
+        cfg.dynamicSmemBytes = ((size_t)pl.ts_nchunk * 32 * TS_WC + 32 * TS_WC + 2 * pl.ts_nchunk * TS_LD +
                                 4 * TS_WC) * sizeof(double) + 16;
         cfg.stream = h->stream;
         cudaLaunchAttribute attr[1];

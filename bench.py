@@ -101,7 +101,9 @@ def cpu_reference_leg(M, P, steps, warmup, budget_s=25.0):
                                       "R_d", "initial_kick")])
     zeta, psi = o.initialise_model(m, seed=1)
     f = np.zeros_like(zeta)
-    threads = oc.max_threads()
+    # all host threads this process may use (torchrun exports OMP_NUM_THREADS=1; the C port sets
+    # its thread count explicitly, so the launcher's default does not throttle the baseline)
+    threads = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else oc.max_threads()
     t = 1
     w = max(1, min(warmup, 1))
     t0 = time.perf_counter()

@@ -22,3 +22,11 @@ print("kernel", pat, "total samples", tot, "sass lines", len(data), "inst execut
 for k, (s, ex, src) in enumerate(data):
     if s > tot * thr:
         print(f"{s:6d} {100*s/tot:5.1f}% [{k:4d}] ex={ex:>9d} {src[:110]}")
+if len(sys.argv) > 4:
+    import collections
+    c = collections.Counter()
+    for s, ex, src in data:
+        toks = src.split()
+        op = toks[1] if toks and toks[0].startswith('@') else (toks[0] if toks else '?')
+        c[op.split('.')[0]] += ex
+    print(c.most_common(25))

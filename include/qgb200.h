@@ -137,6 +137,19 @@ const char* qg_kernel_name(int kernel_id);
 /* Number of kernels launched by this handle since creation (all streams). */
 int64_t qg_launch_count(const qg_handle* h);
 
+/* y-slab domain decomposition of ONE run over `nranks` GPUs of a node, one process per GPU
+ * (new: the reference is a single process).  Create the handle with params.P = the rank's
+ * LOCAL row count (global P / nranks, a multiple of 32, <= 4096); rank r owns global rows
+ * [r * P, (r+1) * P).  After qg_dist_init every call works on the local slab: host arrays are
+ * (M+2, P_local+2, 2, 3) with the neighbours' rows in the ghost rows on download, and
+ * qg_step exchanges halos (ncclSend/ncclRecv ring) and the y-solve carries (ncclAllGather)
+ * on the handle's stream.  qg_nccl_unique_id fills a 128-byte NCCL id on one rank; the host
+ * distributes it (e.g. torch.distributed / MPI broadcast) and every rank passes the same
+ * bytes.  Collective: all ranks must call qg_dist_init, qg_upload_state, qg_step,
+ * qg_download_state and qg_diagnostics together. */
+int qg_nccl_unique_id(void* out128);
+int qg_dist_init(qg_handle* h, int rank, int nranks, const void* unique_id128);
+
 /* Raw device pointers for zero-copy interop (multi-GPU plumbing, torch tensors):
  * which = 0: q, 1: psi, 2: f_store, 3: spectral scratch.  Returns the base pointer, the
  * row pitch in doubles, the left padding (x offset of interior column 0), the ghost-row

@@ -145,7 +145,7 @@ k1_zeta_step(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ C
         // periodic images (update_doubly_periodic_bc!, src/schemes/boundary_conditions.jl:2-13,
         // widened to two ghost cells)
         const bool gl = x < GHOST, gr = x >= a.g.M - GHOST;
-        const bool gb = y < GHOST, gt = y >= a.g.P - GHOST;
+        const bool gb = a.periodic_y && y < GHOST, gt = a.periodic_y && y >= a.g.P - GHOST;
         if (gl) qn[o + a.g.M] = qnew;
         if (gr) qn[o - a.g.M] = qnew;
         if (gb | gt) {
@@ -193,6 +193,7 @@ cudaError_t launch_zeta(Handle* h, int timestep) {
     a.zq = h->zindex(cur, 0, 0);
     a.zpsi = h->zindex(h->pcur, 0, 0);
     a.euler = (timestep == 1 || timestep == 2) ? 1 : 0;   // src/model.jl:161
+    a.periodic_y = h->dist_n > 1 ? 0 : 1;
     const double inv = 1.0 / h->prm.dx;
     a.idx2 = inv * inv;
     a.hdx = 0.5 * inv;

@@ -255,8 +255,10 @@ k2_fft_forward(const FftArgs a, int ngroups_per_member, int ngroups_total) {
             for (int b = 0; b < 4; ++b) {
                 const int k = lt + b * TPR;   // 0 .. N/2 - 1
                 if (k == 0) {
-                    out[0] = s[swz(0)];
+                    const double2 z0 = s[swz(0)];
+                    out[0] = z0;
                     out[half] = s[swz(half)];
+                    a.col0[(int64_t)member * a.pl.P + row] = z0.x;   // Q1[0]: the Poisson k=0 column
                 } else {
                     const double2 X = s[swz(k)], Y = s[swz(N - k)];
                     out[k] = make_double2(0.5 * (X.x + Y.x), 0.5 * (X.y - Y.y));        // Q1[k]
@@ -313,7 +315,7 @@ k4_fft_inverse(const FftArgs a, int ngroups_per_member, int ngroups_total) {
             const double gauge = a.use_gauge ? a.scal[member * 4 + 1] : 0.0;
             double* __restrict__ p1 = a.psi1 + member * a.mstride;
             double* __restrict__ p2 = a.psi2 + member * a.mstride;
-            const bool gb = row < GHOST, gt = row >= P - GHOST;
+            const bool gb = a.periodic_y && row < GHOST, gt = a.periodic_y && row >= P - GHOST;
 #pragma unroll
             for (int e = 0; e < 8; ++e) {
                 const int n = F::out_index(lt, e);
@@ -373,6 +375,7 @@ k2_dft_forward(const FftArgs a) {
     for (int k = threadIdx.x; k <= N / 2; k += blockDim.x) {
         if (k == 0 || 2 * k == N) {
             out[k] = Z[k];
+            if (k == 0) a.col0[(int64_t)member * a.pl.P + row] = Z[0].x;
         } else {
             const double2 A = Z[k], B = Z[N - k];
             out[k] = make_double2(0.5 * (A.x + B.x), 0.5 * (A.y - B.y));
@@ -415,7 +418,7 @@ k4_dft_inverse(const FftArgs a) {
     double* __restrict__ p2 = a.psi2 + member * a.mstride;
     const int M = a.g.M, P = a.g.P;
     const int64_t dyo = (int64_t)P * a.g.pitch;
-    const bool gb = row < GHOST, gt = row >= P - GHOST;
+    const bool gb = a.periodic_y && row < GHOST, gt = a.periodic_y && row >= P - GHOST;
     for (int n = threadIdx.x; n < N; n += blockDim.x) {
         const double t1 = z[n].x - gauge;
         const double o1 = a.A[0] * t1 + a.A[1] * z[n].y;
@@ -511,6 +514,7 @@ cudaError_t launch_fft_forward(Handle* h, const double* q_fields, int /*which*/)
     a.mstride = 2 * h->g.fstride;
     for (int i = 0; i < 4; ++i) a.A[i] = h->prm.Pinv[i];
     a.scal = h->scal;
+    a.col0 = h->col0;
     KernelTimer t(h, QG_K_FFT_FWD);
     if (h->plan.pow2) return dispatch_pow2<true>(h, a);
     const size_t smem = 2 * (size_t)h->plan.M * sizeof(double2);
@@ -533,6 +537,7 @@ cudaError_t launch_fft_inverse(Handle* h, double* psi_fields, int use_gauge) {
     for (int i = 0; i < 4; ++i) a.A[i] = h->prm.Pfwd[i];
     a.scal = h->scal;
     a.use_gauge = use_gauge;
+    a.periodic_y = h->dist_n > 1 ? 0 : 1;
     KernelTimer t(h, QG_K_FFT_INV);
     if (h->plan.pow2) return dispatch_pow2<false>(h, a);
     const size_t smem = 2 * (size_t)h->plan.M * sizeof(double2);

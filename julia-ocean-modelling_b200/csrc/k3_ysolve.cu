@@ -41,16 +41,16 @@ constexpr int PRE_E = 16;   // rows per thread, P <= 16384
 __global__ void __launch_bounds__(PRE_T) k3_pre(const YArgs a) {
     __shared__ double sh[32];
     const int member = blockIdx.x;
-    const int P = a.pl.P;
+    const int P = a.preP;
     const int e = (P + PRE_T - 1) / PRE_T;
-    const double* __restrict__ col = a.S + member * a.sstride;
+    const double* __restrict__ col = a.col0 + (int64_t)member * P;
     const int j0 = threadIdx.x * e;
     double b[PRE_E];
     double loc = 0.0;
 #pragma unroll
     for (int i = 0; i < PRE_E; ++i) {
         const int j = j0 + i;
-        b[i] = (i < e && j < P) ? col[(int64_t)j * a.pl.ncol] : 0.0;
+        b[i] = (i < e && j < P) ? col[j] : 0.0;
         loc += b[i];
     }
     const double total = block_sum(loc, sh);
@@ -88,7 +88,7 @@ __global__ void __launch_bounds__(PRE_T) k3_pre(const YArgs a) {
         if (i < e && j < P) run2 += dm1 + c1[i];
     }
     const double off2 = block_exclusive_scan(run2, sh);
-    double* __restrict__ out = a.k0sol + (int64_t)member * P;
+    double* __restrict__ out = a.k0sol + (int64_t)member * P;   // P == a.preP here
 #pragma unroll
     for (int i = 0; i < PRE_E; ++i) {
         const int j = j0 + i;
@@ -266,7 +266,7 @@ __global__ void __launch_bounds__(512) k3_ysolve(const YArgs a) {
     __syncthreads();
 
     // ---- pass 2: apply carries, backward recurrence, scale, store -----------------------------
-    const double* __restrict__ k0 = a.k0sol + (int64_t)member * P;
+    const double* __restrict__ k0 = a.k0sol + (int64_t)member * a.preP;
     for (int ci = 0; ci < m; ++ci) {
         const int c = cbase + ci;
         const int j0 = c * CH;
@@ -387,7 +387,7 @@ k3_ysolve_tma(const __grid_constant__ CUtensorMap tmS, const YArgs a, int nchunk
 #pragma unroll 4
         for (int i = 0; i < len; ++i) {
             double b = t[i * TS_WC];
-            if (j0 + i == 0) b -= pinv;
+            if (a.row0 + j0 + i == 0) b -= pinv;
             y = fma(r, y, b);
             t[i * TS_WC] = y;
             G = fma(p, y, G);
@@ -453,10 +453,32 @@ k3_ysolve_tma(const __grid_constant__ CUtensorMap tmS, const YArgs a, int nchunk
             FFi[i] = i < CS ? cluster.map_shared_rank(sFF, i)[cl] : 0.0;
             RRi[i] = i < CS ? cluster.map_shared_rank(sRR, i)[cl] : 1.0;
         }
+        if (a.mode == 1) {
+            // y-slab mode, first kernel: fold the cluster's CTAs into one rank-level aggregate
+            // (same affine composition one level up) and stop; the ranks exchange these.
+            double t = 0.0, R = 1.0, X = 0.0, Y = 0.0;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const double Xi = i < CS ? cluster.map_shared_rank(sX, i)[cl] : 0.0;
+                const double Yi = i < CS ? cluster.map_shared_rank(sY, i)[cl] : 0.0;
+                X = fma(R, fma(Yi, t, Xi), X);
+                Y = fma(R, Yi * R, Y);
+                t = fma(RRi[i], t, FFi[i]);
+                R *= RRi[i];
+            }
+            if (cr == 0 && slot == 0 && col0 + cl < ncol) {
+                a.aggr[0 * ncol + col0 + cl] = t;
+                a.aggr[1 * ncol + col0 + cl] = R;
+                a.aggr[2 * ncol + col0 + cl] = X;
+                a.aggr[3 * ncol + col0 + cl] = Y;
+            }
+            continue;
+        }
         double tt = 0.0;
 #pragma unroll
         for (int i = 0; i < 8; ++i) tt = fma(RRi[i], tt, FFi[i]);
-        double as = tt * inv1;   // carry into chunk 0 = y at the last row (cyclic closure)
+        // carry into chunk 0: cyclic closure (y at the last row), or handed in by the rank below
+        double as = a.mode == 2 ? __ldg(a.Ain + gc) : tt * inv1;
         double a_s = 0.0;
         double GGp[8];
 #pragma unroll
@@ -470,7 +492,8 @@ k3_ysolve_tma(const __grid_constant__ CUtensorMap tmS, const YArgs a, int nchunk
         tt = 0.0;
 #pragma unroll
         for (int i = 7; i >= 0; --i) tt = fma(RRi[i], tt, GGp[i]);
-        double b_e = tt * inv1;   // carry into the last chunk = z at row 0 (cyclic closure)
+        // carry into the last chunk: cyclic closure (z at row 0), or handed in by the rank above
+        double b_e = a.mode == 2 ? __ldg(a.Bin + gc) : tt * inv1;
 #pragma unroll
         for (int i = 7; i > 0; --i)
             if (i > cr) b_e = fma(RRi[i], b_e, GGp[i]);
@@ -502,12 +525,16 @@ k3_ysolve_tma(const __grid_constant__ CUtensorMap tmS, const YArgs a, int nchunk
         }
     }
     cluster.barrier_arrive();   // remote reads are done; matched by barrier_wait() before exit
+    if (a.mode == 1) {
+        cluster.barrier_wait();
+        return;
+    }
     __syncthreads();
 
     // ---- pass 2: add the carry, backward recurrence, scale, store --------------------------------
     {
         const double A = mine ? sF[chunk * TS_LD + l] : 0.0, B = mine ? sG[chunk * TS_LD + l] : 0.0;
-        const double* __restrict__ k0 = a.k0sol + (int64_t)member * P;
+        const double* __restrict__ k0 = a.k0sol + (int64_t)member * a.preP + a.row0;
         double* __restrict__ out = a.S + member * a.sstride + (int64_t)j0 * ncol + ccol;
         double z = B;
 #pragma unroll 4
@@ -522,14 +549,128 @@ k3_ysolve_tma(const __grid_constant__ CUtensorMap tmS, const YArgs a, int nchunk
     cluster.barrier_wait();   // distributed shared memory must outlive every remote read
 }
 
+// y-slab mode: cyclic closure over the ranks.  aggr_all[g][4][ncol] holds every rank's
+// (FF, RR, X, Y); thread per column computes the forward carry entering this rank from below
+// (Ain) and the backward carry entering it from above (Bin).  Same algebra as the CTA level.
+__global__ void __launch_bounds__(256)
+k3_rank_closure(const double* __restrict__ aggr_all, int nranks, int rank, int ncol,
+                const double* __restrict__ inv1mrP, double* __restrict__ Ain, double* __restrict__ Bin) {
+    const int col = blockIdx.x * blockDim.x + threadIdx.x;
+    if (col >= ncol) return;
+    double FFi[8], RRi[8], Xi[8], Yi[8];
+#pragma unroll
+    for (int g = 0; g < 8; ++g) {
+        const bool in = g < nranks;
+        const double* p = aggr_all + (size_t)(in ? g : 0) * 4 * ncol + col;
+        FFi[g] = in ? p[0] : 0.0;
+        RRi[g] = in ? p[ncol] : 1.0;
+        Xi[g] = in ? p[2 * ncol] : 0.0;
+        Yi[g] = in ? p[3 * ncol] : 0.0;
+    }
+    const double inv1 = inv1mrP[col];
+    double tt = 0.0;
+#pragma unroll
+    for (int g = 0; g < 8; ++g) tt = fma(RRi[g], tt, FFi[g]);
+    double as = tt * inv1, a_s = 0.0;
+    double GGp[8];
+#pragma unroll
+    for (int g = 0; g < 8; ++g) {
+        GGp[g] = fma(Yi[g], as, Xi[g]);
+        if (g == rank) a_s = as;
+        as = fma(RRi[g], as, FFi[g]);
+    }
+    tt = 0.0;
+#pragma unroll
+    for (int g = 7; g >= 0; --g) tt = fma(RRi[g], tt, GGp[g]);
+    double b_e = tt * inv1;
+#pragma unroll
+    for (int g = 7; g > 0; --g)
+        if (g > rank) b_e = fma(RRi[g], b_e, GGp[g]);
+    Ain[col] = a_s;
+    Bin[col] = b_e;
+}
+
+static cudaError_t launch_tma_kernel(Handle* h, const YArgs& a) {
+    const Plan& pl = h->plan;
+    const int nslab = (pl.ncol + TS_WC - 1) / TS_WC;
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(nslab * pl.ts_CS, h->nm, 1);
+    cfg.blockDim = dim3(((16 * pl.ts_nchunk + 31) / 32) * 32, 1, 1);
+    cfg.dynamicSmemBytes = ((size_t)pl.ts_nchunk * 32 * TS_WC + 32 * TS_WC + 2 * pl.ts_nchunk * TS_LD +
+                            4 * TS_WC) * sizeof(double) + 16;
+    cfg.stream = h->stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = pl.ts_CS;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    static size_t configured = 0;
+    if (cfg.dynamicSmemBytes > configured) {
+        cudaError_t e = cudaFuncSetAttribute(k3_ysolve_tma, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             (int)cfg.dynamicSmemBytes);
+        if (e != cudaSuccess) return e;
+        configured = cfg.dynamicSmemBytes;
+    }
+    KernelTimer t(h, QG_K_YSOLVE);
+    return cudaLaunchKernelEx(&cfg, k3_ysolve_tma, h->tm_S, a, pl.ts_nchunk);
+}
+
+// y-slab mode: gather the k=0 column, solve it redundantly on every rank, sweep + exchange the
+// rank-level carry aggregates, close the recurrences over the ranks, apply.
+static cudaError_t launch_ysolve_dist(Handle* h, int pinned) {
+    YArgs a{};
+    a.pl = h->plan;
+    a.S = h->S;
+    a.sstride = (int64_t)h->plan.P * h->plan.ncol;
+    a.scal = h->scal;
+    a.pinned = pinned;
+    a.row0 = h->dist_rank * h->plan.P;
+    a.preP = h->Pglob;
+    a.col0 = h->col0_full;
+    a.k0sol = h->k0sol_full;
+    a.aggr = h->aggr;
+    a.Ain = h->carry_in;
+    a.Bin = h->carry_in + h->plan.ncol;
+    cudaError_t e = dist_allgather(h, h->col0, h->col0_full, (size_t)h->plan.P);
+    if (e != cudaSuccess) return e;
+    {
+        KernelTimer t(h, QG_K_YPRE);
+        k3_pre<<<1, PRE_T, 0, h->stream>>>(a);
+    }
+    if ((e = cudaGetLastError()) != cudaSuccess) return e;
+    a.mode = 1;
+    if ((e = launch_tma_kernel(h, a)) != cudaSuccess) return e;
+    if ((e = dist_allgather(h, h->aggr, h->aggr_all, (size_t)4 * h->plan.ncol)) != cudaSuccess) return e;
+    {
+        KernelTimer t(h, QG_K_GAUGE);
+        k3_rank_closure<<<(h->plan.ncol + 255) / 256, 256, 0, h->stream>>>(
+            h->aggr_all, h->dist_n, h->dist_rank, h->plan.ncol, h->plan.inv1mrP, h->carry_in,
+            h->carry_in + h->plan.ncol);
+    }
+    if ((e = cudaGetLastError()) != cudaSuccess) return e;
+    a.mode = 2;
+    if ((e = launch_tma_kernel(h, a)) != cudaSuccess) return e;
+    if (h->dist_rank == 0) {   // global row 0 lives on rank 0
+        KernelTimer t(h, QG_K_GAUGE);
+        k3_gauge<<<1, 256, 0, h->stream>>>(a);
+        if ((e = cudaGetLastError()) != cudaSuccess) return e;
+    }
+    return dist_broadcast(h, h->scal, 4, 0);
+}
+
 cudaError_t launch_ysolve(Handle* h, int pinned, int /*unused*/) {
     YArgs a{};
     a.pl = h->plan;
     a.S = h->S;
     a.sstride = (int64_t)h->plan.P * h->plan.ncol;
+    if (h->dist_n > 1) return launch_ysolve_dist(h, pinned);
     a.k0sol = h->k0sol;
     a.scal = h->scal;
     a.pinned = pinned;
+    a.col0 = h->col0;
+    a.preP = h->plan.P;
     {
         KernelTimer t(h, QG_K_YPRE);
         k3_pre<<<h->nm, PRE_T, 0, h->stream>>>(a);
@@ -537,30 +678,7 @@ cudaError_t launch_ysolve(Handle* h, int pinned, int /*unused*/) {
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
     if (h->plan.ts_ok) {
-        const Plan& pl = h->plan;
-        const int nslab = (pl.ncol + TS_WC - 1) / TS_WC;
-        cudaLaunchConfig_t cfg{};
-        cfg.gridDim = dim3(nslab * pl.ts_CS, h->nm, 1);
-        cfg.blockDim = dim3(((16 * pl.ts_nchunk + 31) / 32) * 32, 1, 1);
-        cfg.dynamicSmemBytes = ((size_t)pl.ts_nchunk * 32 * TS_WC + 32 * TS_WC + 2 * pl.ts_nchunk * TS_LD +
-                                4 * TS_WC) * sizeof(double) + 16;
-        cfg.stream = h->stream;
-        cudaLaunchAttribute attr[1];
-        attr[0].id = cudaLaunchAttributeClusterDimension;
-        attr[0].val.clusterDim.x = pl.ts_CS;
-        attr[0].val.clusterDim.y = 1;
-        attr[0].val.clusterDim.z = 1;
-        cfg.attrs = attr;
-        cfg.numAttrs = 1;
-        static size_t configured = 0;
-        if (cfg.dynamicSmemBytes > configured) {
-            e = cudaFuncSetAttribute(k3_ysolve_tma, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     (int)cfg.dynamicSmemBytes);
-            if (e != cudaSuccess) return e;
-            configured = cfg.dynamicSmemBytes;
-        }
-        KernelTimer t(h, QG_K_YSOLVE);
-        e = cudaLaunchKernelEx(&cfg, k3_ysolve_tma, h->tm_S, a, pl.ts_nchunk);
+        e = launch_tma_kernel(h, a);
     } else {
         const Plan& pl = h->plan;
         const int nslab = (pl.ncol + 31) / 32;

@@ -54,8 +54,7 @@ __global__ void k_unpack(const double* __restrict__ host, double* __restrict__ d
 }
 
 __global__ void k_pack(const double* __restrict__ dev, double* __restrict__ host, Geom g, int nm,
-                       int slot0, int s1, int s2, const double* __restrict__ shift, double sh0,
-                       double sh1) {
+                       int slot0, int s1, int s2, int y_from_ghost) {
     const int ih = blockIdx.x * blockDim.x + threadIdx.x;   // 0 .. M+1 (host index incl. ghost)
     const int jh = blockIdx.y;                              // 0 .. P+1
     if (ih >= g.M + 2) return;
@@ -64,10 +63,12 @@ __global__ void k_pack(const double* __restrict__ dev, double* __restrict__ host
     z >>= 1;
     const int member = z % nm, level = z / nm;
     const int slot = level == 0 ? slot0 : (level == 1 ? s1 : s2);
-    const int i = ((ih - 1) % g.M + g.M) % g.M, j = ((jh - 1) % g.P + g.P) % g.P;
+    // x wraps locally; y wraps locally too unless this is a y-slab, whose ghost rows hold the
+    // neighbours' rows (filled by the halo exchange)
+    const int i = ((ih - 1) % g.M + g.M) % g.M;
+    const int j = y_from_ghost ? jh - 1 : ((jh - 1) % g.P + g.P) % g.P;
     const int64_t hs = (int64_t)(g.M + 2) * (g.P + 2);
     double v = dev[((int64_t)(slot * nm + member) * 2 + layer) * g.fstride + g.at(i, j)];
-    (void)shift; (void)sh0; (void)sh1;
     host[(int64_t)member * 6 * hs + (int64_t)(level * 2 + layer) * hs + (int64_t)jh * (g.M + 2) + ih] = v;
 }
 
@@ -203,7 +204,7 @@ cudaError_t build_plan(Handle* h) {
         long double r = 0.0L;
         const bool singular = !(e > 0.0L);
         if (!singular) r = 2.0L / ((2.0L + e) + sqrtl(e * (e + 4.0L)));
-        const long double r32 = powl(r, 32), rL = powl(r, pl.lenLast), rP = powl(r, P);
+        const long double r32 = powl(r, 32), rL = powl(r, pl.lenLast), rP = powl(r, h->Pglob > 0 ? h->Pglob : P);
         const long double geo32 = singular ? 0.0L : r * (1.0L - r32 * r32) / (1.0L - r * r);
         const long double geoL = singular ? 0.0L : r * (1.0L - rL * rL) / (1.0L - r * r);
         rtab[col] = (double)r;
@@ -309,6 +310,13 @@ static int do_evolve_psi(Handle* h) {
     QG_CUDA(h, launch_ysolve(h, 1, 0));
     QG_CUDA(h, launch_fft_inverse(h, h->field(h->psi, nxt, 0, 0), 1));
     h->pcur = nxt;
+    if (h->dist_n > 1) QG_CUDA(h, dist_halo_exchange(h, h->psi, nxt));
+    return QG_OK;
+}
+
+static int do_evolve_zeta(Handle* h, int timestep) {
+    QG_CUDA(h, launch_zeta(h, timestep));
+    if (h->dist_n > 1) QG_CUDA(h, dist_halo_exchange(h, h->q, h->qcur));
     return QG_OK;
 }
 
@@ -387,6 +395,8 @@ int qg_create(const qg_params* p, int device, int nmembers, void* stream, qg_han
     QG_TRY(cudaMemsetAsync(h->f, 0, fbytes, h->stream));
     QG_TRY(cudaMalloc((void**)&h->S, (size_t)nmembers * p->P * 2 * p->M * sizeof(double)));
     QG_TRY(cudaMalloc((void**)&h->k0sol, (size_t)nmembers * p->P * sizeof(double)));
+    QG_TRY(cudaMalloc((void**)&h->col0, (size_t)nmembers * p->P * sizeof(double)));
+    h->Pglob = p->P;
     QG_TRY(cudaMalloc((void**)&h->scal, (size_t)nmembers * 4 * sizeof(double)));
     QG_TRY(cudaMemsetAsync(h->scal, 0, (size_t)nmembers * 4 * sizeof(double), h->stream));
     h->diag_blocks = p->P < 592 ? p->P : 592;
@@ -411,7 +421,9 @@ int qg_destroy(qg_handle* h) {
     if (!h) return QG_OK;
     cudaSetDevice(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
+    dist_destroy(h);
     free_plan(h);
+    cudaFree(h->col0);
     cudaFree(h->q); cudaFree(h->psi); cudaFree(h->f); cudaFree(h->S); cudaFree(h->k0sol);
     cudaFree(h->scal); cudaFree(h->stage); cudaFree(h->diag_part);
     for (cudaEvent_t e : h->evpool) cudaEventDestroy(e);
@@ -436,16 +448,20 @@ static int upload_one(qg_handle* h, const double* host, double* dev, int cur) {
         k_unpack<<<grid, block, 0, h->stream>>>(h->stage, dev, h->g, h->nm, cur, (cur + 2) % 3, (cur + 1) % 3);
     }
     QG_CUDA(h, cudaGetLastError());
+    if (h->dist_n > 1)   // y-slab: the ghost rows are the neighbours' rows, not local periodic images
+        for (int s = 0; s < 3; ++s) QG_CUDA(h, dist_halo_exchange(h, dev, s));
     return QG_OK;
 }
 
-static int download_one(qg_handle* h, const double* dev, double* host, int cur) {
+static int download_one(qg_handle* h, double* dev, double* host, int cur) {
     const size_t n = (size_t)h->nm * 6 * (h->g.M + 2) * (h->g.P + 2);
+    if (h->dist_n > 1)
+        for (int s = 0; s < 3; ++s) QG_CUDA(h, dist_halo_exchange(h, dev, s));
     dim3 block(128), grid((h->g.M + 2 + 127) / 128, h->g.P + 2, 3 * h->nm * 2);
     {
         KernelTimer t(h, QG_K_PACK);
         k_pack<<<grid, block, 0, h->stream>>>(dev, h->stage, h->g, h->nm, cur, (cur + 2) % 3, (cur + 1) % 3,
-                                              nullptr, 0.0, 0.0);
+                                              h->dist_n > 1 ? 1 : 0);
     }
     QG_CUDA(h, cudaGetLastError());
     QG_CUDA(h, cudaMemcpyAsync(host, h->stage, n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
@@ -494,8 +510,7 @@ int qg_evolve_zeta(qg_handle* h, int timestep) {
     if (!h->have_state) return fail(h, QG_ERR_STATE, "qg_evolve_zeta: no state uploaded");
     if (timestep < 1) return fail(h, QG_ERR_INVALID, "qg_evolve_zeta: timestep is 1-based");
     QG_CUDA(h, cudaSetDevice(h->device));
-    QG_CUDA(h, launch_zeta(h, timestep));
-    return QG_OK;
+    return do_evolve_zeta(h, timestep);
 }
 
 int qg_evolve_psi(qg_handle* h) {
@@ -511,8 +526,9 @@ int qg_step(qg_handle* h, int first_timestep, int nsteps) {
     if (first_timestep < 1 || nsteps < 0) return fail(h, QG_ERR_INVALID, "qg_step: bad timestep range");
     QG_CUDA(h, cudaSetDevice(h->device));
     for (int t = first_timestep; t < first_timestep + nsteps; ++t) {
-        QG_CUDA(h, launch_zeta(h, t));
-        int rc = do_evolve_psi(h);
+        int rc = do_evolve_zeta(h, t);
+        if (rc) return rc;
+        rc = do_evolve_psi(h);
         if (rc) return rc;
     }
     return QG_OK;
@@ -531,6 +547,8 @@ int qg_diagnostics(qg_handle* h, double* energy, double* enstrophy) {
     if (!h->have_state) return fail(h, QG_ERR_STATE, "qg_diagnostics: no state uploaded");
     QG_CUDA(h, cudaSetDevice(h->device));
     QG_CUDA(h, launch_diag(h));
+    if (h->dist_n > 1)   // local sums -> domain sums
+        QG_CUDA(h, dist_allreduce_sum(h, h->diag_part + (int64_t)h->nm * h->diag_blocks * 2, 2 * (size_t)h->nm));
     std::vector<double> out(2 * h->nm);
     QG_CUDA(h, cudaMemcpyAsync(out.data(), h->diag_part + (int64_t)h->nm * h->diag_blocks * 2,
                                out.size() * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
@@ -578,7 +596,7 @@ int qg_solve(qg_handle* h, int pinned, const double* f, double* u) {
     if (e == cudaSuccess) {
         dim3 block(128), grid((g.M + 2 + 127) / 128, g.P + 2, 2);
         KernelTimer t(h, QG_K_PACK);
-        k_pack<<<grid, block, 0, h->stream>>>(tmp + 2 * g.fstride, h->stage, g, 1, 0, 0, 0, nullptr, 0.0, 0.0);
+        k_pack<<<grid, block, 0, h->stream>>>(tmp + 2 * g.fstride, h->stage, g, 1, 0, 0, 0, 0);
         e = cudaGetLastError();
     }
     if (e == cudaSuccess)
@@ -588,6 +606,33 @@ int qg_solve(qg_handle* h, int pinned, const double* f, double* u) {
     h->prm = saved;
     cudaFree(tmp);
     QG_CUDA(h, e);
+    return QG_OK;
+}
+
+int qg_nccl_unique_id(void* out128) {
+    if (!out128) return QG_ERR_INVALID;
+    std::string err;
+    int rc = dist_unique_id(out128, &err);
+    if (rc) g_create_error = err;
+    return rc;
+}
+
+int qg_dist_init(qg_handle* h, int rank, int nranks, const void* unique_id128) {
+    if (!h || !unique_id128) return QG_ERR_INVALID;
+    if (h->dist_n > 1) return fail(h, QG_ERR_STATE, "qg_dist_init: already initialised");
+    if (nranks < 2 || nranks > 8 || rank < 0 || rank >= nranks)
+        return fail(h, QG_ERR_INVALID, "qg_dist_init: need 2 <= nranks <= 8 and 0 <= rank < nranks");
+    if (h->nm != 1) return fail(h, QG_ERR_INVALID, "qg_dist_init: y-slab mode takes one member per handle");
+    if (h->g.P % 32 != 0 || !h->plan.ts_ok)
+        return fail(h, QG_ERR_INVALID, "qg_dist_init: local row count must be a multiple of 32 and at most 4096");
+    if ((int64_t)h->g.P * nranks > 16384) return fail(h, QG_ERR_INVALID, "qg_dist_init: global P > 16384");
+    QG_CUDA(h, cudaSetDevice(h->device));
+    int rc = dist_init(h, rank, nranks, unique_id128);
+    if (rc) return rc;
+    // the cyclic closure now spans the global row count: rebuild the coefficient tables
+    free_plan(h);
+    QG_CUDA(h, build_plan(h));
+    h->have_state = false;
     return QG_OK;
 }
 

@@ -1,0 +1,154 @@
+// y-slab decomposition of one run over several GPUs: NCCL plumbing.
+//
+// The reference is a single process (no collective of any kind), so everything
+// here is new.  One process per GPU; rank g owns P_global / G consecutive rows with every x (the
+// x-FFT stays local).  Per time step the ranks exchange
+//   - two halo rows of q after K1 and of psi after K4, up and down the periodic ring
+//     (ncclSend / ncclRecv inside one group; the biharmonic term reaches +-2 rows),
+//   - the k = 0 Poisson column (all-gather of P_local doubles) and the rank-level carry
+//     aggregates of the y-solve (all-gather of 4 * 2M doubles) instead of the all-to-all
+//     transpose a tridiagonal solver would need,
+//   - the gauge constant (broadcast of 4 doubles from rank 0).
+// All calls are enqueued on the handle's stream, so the step loop never synchronises the host.
+// NCCL is loaded with dlopen at qg_dist_init: the single-GPU path has no NCCL dependency.
+#include <dlfcn.h>
+#include <nccl.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "qg_internal.cuh"
+
+namespace qg {
+
+struct NcclApi {
+    void* lib = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Broadcast)(const void*, void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Send)(const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*GroupStart)() = nullptr;
+    ncclResult_t (*GroupEnd)() = nullptr;
+    const char* (*GetErrorString)(ncclResult_t) = nullptr;
+};
+
+static NcclApi g_nccl;
+
+static const char* load_nccl() {
+    if (g_nccl.lib) return nullptr;
+    const char* names[] = {"libnccl.so.2", "libnccl.so"};
+    void* lib = nullptr;
+    for (const char* n : names) {
+        lib = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+        if (lib) break;
+    }
+    if (!lib) return "libnccl.so.2 not found (dlopen)";
+#define QG_SYM(field, name)                                           \
+    *(void**)(&g_nccl.field) = dlsym(lib, name);                      \
+    if (!g_nccl.field) return "libnccl is missing symbol " name;
+    QG_SYM(GetUniqueId, "ncclGetUniqueId")
+    QG_SYM(CommInitRank, "ncclCommInitRank")
+    QG_SYM(CommDestroy, "ncclCommDestroy")
+    QG_SYM(AllGather, "ncclAllGather")
+    QG_SYM(Broadcast, "ncclBroadcast")
+    QG_SYM(AllReduce, "ncclAllReduce")
+    QG_SYM(Send, "ncclSend")
+    QG_SYM(Recv, "ncclRecv")
+    QG_SYM(GroupStart, "ncclGroupStart")
+    QG_SYM(GroupEnd, "ncclGroupEnd")
+    QG_SYM(GetErrorString, "ncclGetErrorString")
+#undef QG_SYM
+    g_nccl.lib = lib;
+    return nullptr;
+}
+
+static cudaError_t nccl_check(Handle* h, ncclResult_t r, const char* what) {
+    if (r == ncclSuccess) return cudaSuccess;
+    char b[256];
+    snprintf(b, sizeof(b), "NCCL %s failed: %s", what, g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "?");
+    h->err = b;
+    return cudaErrorUnknown;
+}
+
+cudaError_t dist_allgather(Handle* h, const double* send, double* recv, size_t count) {
+    return nccl_check(h, g_nccl.AllGather(send, recv, count, ncclFloat64, (ncclComm_t)h->nccl, h->stream), "AllGather");
+}
+
+cudaError_t dist_broadcast(Handle* h, double* buf, size_t count, int root) {
+    return nccl_check(h, g_nccl.Broadcast(buf, buf, count, ncclFloat64, root, (ncclComm_t)h->nccl, h->stream), "Broadcast");
+}
+
+cudaError_t dist_allreduce_sum(Handle* h, double* buf, size_t count) {
+    return nccl_check(h, g_nccl.AllReduce(buf, buf, count, ncclFloat64, ncclSum, (ncclComm_t)h->nccl, h->stream), "AllReduce");
+}
+
+// Fill the two ghost rows above and below the local rows of every field of one slot with the
+// neighbours' boundary rows (periodic ring).  Whole padded rows travel, so the x ghosts and the
+// corners arrive with them.
+cudaError_t dist_halo_exchange(Handle* h, double* base, int slot) {
+    const Geom& g = h->g;
+    const int up = (h->dist_rank + 1) % h->dist_n, down = (h->dist_rank + h->dist_n - 1) % h->dist_n;
+    const size_t n = (size_t)GHOST * g.pitch;
+    ncclComm_t comm = (ncclComm_t)h->nccl;
+    ncclResult_t r = g_nccl.GroupStart();
+    for (int m = 0; m < h->nm && r == ncclSuccess; ++m)
+        for (int l = 0; l < 2 && r == ncclSuccess; ++l) {
+            double* f = h->field(base, slot, m, l);
+            double* first = f + (int64_t)YPAD * g.pitch;                     // local rows 0, 1
+            double* last = f + (int64_t)(YPAD + g.P - GHOST) * g.pitch;      // local rows P-2, P-1
+            double* ghost_lo = f;                                            // rows -2, -1
+            double* ghost_hi = f + (int64_t)(YPAD + g.P) * g.pitch;          // rows P, P+1
+            r = g_nccl.Send(first, n, ncclFloat64, down, comm, h->stream);
+            if (r == ncclSuccess) r = g_nccl.Send(last, n, ncclFloat64, up, comm, h->stream);
+            if (r == ncclSuccess) r = g_nccl.Recv(ghost_hi, n, ncclFloat64, up, comm, h->stream);
+            if (r == ncclSuccess) r = g_nccl.Recv(ghost_lo, n, ncclFloat64, down, comm, h->stream);
+        }
+    ncclResult_t r2 = g_nccl.GroupEnd();
+    if (r != ncclSuccess) return nccl_check(h, r, "Send/Recv");
+    return nccl_check(h, r2, "GroupEnd");
+}
+
+void dist_destroy(Handle* h) {
+    if (h->nccl && g_nccl.CommDestroy) g_nccl.CommDestroy((ncclComm_t)h->nccl);
+    h->nccl = nullptr;
+    cudaFree(h->col0_full); cudaFree(h->k0sol_full); cudaFree(h->aggr); cudaFree(h->aggr_all); cudaFree(h->carry_in);
+    h->col0_full = h->k0sol_full = h->aggr = h->aggr_all = h->carry_in = nullptr;
+}
+
+int dist_unique_id(void* out128, std::string* err) {
+    const char* e = load_nccl();
+    if (e) { *err = e; return QG_ERR_CUDA; }
+    ncclUniqueId id;
+    ncclResult_t r = g_nccl.GetUniqueId(&id);
+    if (r != ncclSuccess) { *err = std::string("ncclGetUniqueId: ") + g_nccl.GetErrorString(r); return QG_ERR_CUDA; }
+    static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is 128 bytes");
+    memcpy(out128, &id, 128);
+    return QG_OK;
+}
+
+int dist_init(Handle* h, int rank, int nranks, const void* id128) {
+    const char* e = load_nccl();
+    if (e) { h->err = e; return QG_ERR_CUDA; }
+    ncclUniqueId id;
+    memcpy(&id, id128, 128);
+    ncclComm_t comm = nullptr;
+    ncclResult_t r = g_nccl.CommInitRank(&comm, nranks, id, rank);
+    if (r != ncclSuccess) { h->err = std::string("ncclCommInitRank: ") + g_nccl.GetErrorString(r); return QG_ERR_CUDA; }
+    h->nccl = comm;
+    h->dist_n = nranks;
+    h->dist_rank = rank;
+    h->Pglob = h->g.P * nranks;
+    const size_t ncol = h->plan.ncol;
+    cudaError_t ce = cudaMalloc((void**)&h->col0_full, (size_t)h->Pglob * sizeof(double));
+    if (ce == cudaSuccess) ce = cudaMalloc((void**)&h->k0sol_full, (size_t)h->Pglob * sizeof(double));
+    if (ce == cudaSuccess) ce = cudaMalloc((void**)&h->aggr, 4 * ncol * sizeof(double));
+    if (ce == cudaSuccess) ce = cudaMalloc((void**)&h->aggr_all, (size_t)nranks * 4 * ncol * sizeof(double));
+    if (ce == cudaSuccess) ce = cudaMalloc((void**)&h->carry_in, 2 * ncol * sizeof(double));
+    if (ce != cudaSuccess) { h->err = std::string("qg_dist_init: ") + cudaGetErrorString(ce); return QG_ERR_NOMEM; }
+    return QG_OK;
+}
+
+}  // namespace qg

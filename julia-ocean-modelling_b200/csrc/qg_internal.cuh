@@ -45,6 +45,7 @@ struct ZetaArgs {
     double* qn;         // new PV (output)
     int zq, zpsi;       // first field index (tensor-map z coordinate) of q / psi inputs
     int euler;          // 1: steps 1-2 (no history read)
+    int periodic_y;     // 1: write the y ghost images locally; 0: y-slab mode
     double idx2;        // (1/dx)^2
     double hdx;         // 0.5*(1/dx)
     double i12dx2;      // 1 / (3*4*dx^2)
@@ -85,6 +86,8 @@ struct FftArgs {
     double A[4];       // forward: P_inv; inverse: P (row-major)
     const double* scal;  // per member: [0] = sum of the Poisson k=0 column, [1] = gauge
     int use_gauge;
+    int periodic_y;      // 1: write the y ghost images locally; 0: y-slab mode (halo exchange fills them)
+    double* col0;        // forward: compact copy of the Poisson k=0 column, [member * P + row]
 };
 
 struct YArgs {
@@ -94,6 +97,18 @@ struct YArgs {
     double* k0sol;      // per member: P doubles, solution of the singular k=0 Poisson column
     double* scal;       // per member: 4 doubles
     int pinned;         // 1: apply the reference's node-(0,0) pin (src/schemes/laplacian.jl:66-75)
+    // k=0 Poisson column, compact: col0[member * preP + j]; k0sol has the same indexing
+    const double* col0;
+    int preP;           // rows of the column handed to k3_pre (global row count in y-slab mode)
+    int row0;           // global row index of local row 0 (0 unless y-slab mode)
+    // y-slab mode (one run split over ranks): mode 1 = sweep + write the rank-level carry
+    // aggregates (FF, RR, X, Y)[ncol] and stop; mode 2 = solve with the carries entering the
+    // rank from its neighbours given (Ain = forward carry into the first local row, Bin =
+    // backward carry into the last local row).  mode 0 = cyclic over the local rows.
+    int mode;
+    double* aggr;       // [4][ncol]
+    const double* Ain;  // [ncol]
+    const double* Bin;  // [ncol]
 };
 
 struct Handle;
@@ -103,6 +118,13 @@ cudaError_t launch_zeta(Handle* h, int timestep);
 cudaError_t launch_fft_forward(Handle* h, const double* q_fields, int which_pinv);
 cudaError_t launch_fft_inverse(Handle* h, double* psi_fields, int use_gauge);
 cudaError_t launch_ysolve(Handle* h, int pinned, int do_poisson_only);
+cudaError_t dist_halo_exchange(Handle* h, double* base, int slot);   // qg_dist.cu
+cudaError_t dist_allgather(Handle* h, const double* send, double* recv, size_t count);
+cudaError_t dist_broadcast(Handle* h, double* buf, size_t count, int root);
+cudaError_t dist_allreduce_sum(Handle* h, double* buf, size_t count);
+void dist_destroy(Handle* h);
+int dist_init(Handle* h, int rank, int nranks, const void* id128);
+int dist_unique_id(void* out128, std::string* err);
 cudaError_t launch_unpack(Handle* h, const double* host_like, double* dev_fields, int slot_of_level0,
                           int nlevels);
 cudaError_t launch_pack(Handle* h, const double* dev_fields, double* host_like, int cur);
@@ -132,6 +154,16 @@ struct Handle {
     double* k0sol = nullptr;         // [nm][P]
     double* scal = nullptr;          // [nm][4]
     double* stage = nullptr;         // host-layout staging (3*2*(M+2)*(P+2)*nm doubles)
+    double* col0 = nullptr;          // [nm][P] compact Poisson k=0 column (written by K2)
+    // ---- y-slab decomposition of one run over several GPUs (qg_dist_init) ----
+    int dist_n = 1, dist_rank = 0;
+    int Pglob = 0;                   // global row count (= P when not distributed)
+    void* nccl = nullptr;            // ncclComm_t
+    double* col0_full = nullptr;     // [Pglob] gathered k=0 column
+    double* k0sol_full = nullptr;    // [Pglob]
+    double* aggr = nullptr;          // [4][ncol] this rank's carry aggregates
+    double* aggr_all = nullptr;      // [dist_n][4][ncol]
+    double* carry_in = nullptr;      // [2][ncol]  Ain, Bin
     double* diag_part = nullptr;     // partial sums for diagnostics
     int diag_blocks = 0;
     int64_t launches = 0;

@@ -10,3 +10,4 @@ from .model import (DAY, KM, MINUTES, YEAR, BaroclinicModel, P_inv_matrix, P_mat
                     close_sessions, evolve_psi, evolve_zeta, get_helmholtz_cholesky, get_poisson_cholesky,
                     initialise_model, make_params, ratio_term, run_model_no_output,
                     sp_solve_modified_helmholtz, sp_solve_poisson, update_doubly_periodic_bc)
+from . import slab  # noqa: E402,F401

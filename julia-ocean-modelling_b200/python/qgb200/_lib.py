@@ -51,6 +51,8 @@ SYMBOLS = {
     "qg_kernel_times": (C.c_int, [_P, _D, C.POINTER(C.c_int64)]),
     "qg_kernel_name": (C.c_char_p, [C.c_int]),
     "qg_launch_count": (C.c_int64, [_P]),
+    "qg_nccl_unique_id": (C.c_int, [_P]),
+    "qg_dist_init": (C.c_int, [_P, C.c_int, C.c_int, _P]),
     "qg_device_layout": (C.c_int, [_P, C.c_int, C.POINTER(_P), C.POINTER(C.c_int64),
                                    C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
 }

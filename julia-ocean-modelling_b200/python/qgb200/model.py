@@ -193,6 +193,22 @@ class Session:
     def _ptr(a):
         return None if a is None else C.c_void_p(a.ctypes.data)
 
+    # -- y-slab decomposition over several GPUs -----------------------------------------
+    @staticmethod
+    def nccl_unique_id():
+        """128-byte NCCL id (create on one rank, broadcast to the others)."""
+        buf = C.create_string_buffer(128)
+        lib = _lib.load()
+        rc = lib.qg_nccl_unique_id(buf)
+        if rc != 0:
+            raise QGError(rc, lib.qg_last_error(None).decode())
+        return buf.raw
+
+    def dist_init(self, rank, nranks, unique_id):
+        """Turn this session into rank `rank` of a y-slab decomposition (model.P = local rows)."""
+        assert len(unique_id) == 128
+        self._ck(self._lib.qg_dist_init(self._h, int(rank), int(nranks), C.c_char_p(unique_id)))
+
     # -- state transfer -----------------------------------------------------------------
     def upload(self, zeta=None, psi=None, f_store=None):
         for name, a in (("zeta", zeta), ("psi", psi), ("f_store", f_store)):

@@ -91,25 +91,26 @@ struct RowFft {
     double2 w8[NW8];   // base twiddle of radix-8 pass p = 1 .. NB8-1
     double2 wr[4];     // base twiddles of the remainder pass (2 butterflies radix-4, 4 radix-2)
 
-    __device__ __forceinline__ void init(const double2* __restrict__ tw, int lt) {
+    // `stride`: the table holds exp(-2 pi i n / (stride * N))
+    __device__ __forceinline__ void init(const double2* __restrict__ tw, int lt, int stride = 1) {
         int Ns = 8;
 #pragma unroll
         for (int p = 1; p < NB8; ++p) {
             const int k = lt & (Ns - 1);
-            w8[p - 1] = twid<SIGN>(tw, k * (N / (Ns * 8)));
+            w8[p - 1] = twid<SIGN>(tw, stride * (k * (N / (Ns * 8))));
             Ns *= 8;
         }
         if (REM == 2) {
 #pragma unroll
             for (int b = 0; b < 2; ++b) {
                 const int j = lt + b * TPR;
-                wr[b] = twid<SIGN>(tw, (j & (Ns - 1)) * (N / (Ns * 4)));
+                wr[b] = twid<SIGN>(tw, stride * ((j & (Ns - 1)) * (N / (Ns * 4))));
             }
         } else if (REM == 1) {
 #pragma unroll
             for (int b = 0; b < 4; ++b) {
                 const int j = lt + b * TPR;
-                wr[b] = twid<SIGN>(tw, (j & (Ns - 1)) * (N / (Ns * 2)));
+                wr[b] = twid<SIGN>(tw, stride * ((j & (Ns - 1)) * (N / (Ns * 2))));
             }
         }
     }
@@ -345,6 +346,156 @@ k4_fft_inverse(const FftArgs a, int ngroups_per_member, int ngroups_total) {
 }
 
 // ---------------------------------------------------------------------------------------
+// M = 2N too long for one shared-memory row (M = 16384: 256 KB as a packed complex row).
+// One CTA per (row, modal field) forward / (row, layer) inverse runs a real transform of
+// length M as a complex transform of length N = M/2 on z[n] = x[2n] + i x[2n+1] plus the
+// usual split  X[k] = E[k] + W^k O[k],  W = exp(-2 pi i / M).  The projections are linear,
+// so they are applied in physical space before the forward transform and in spectral space
+// before the inverse one (each CTA reads both inputs).  Same spectral layout as above.
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ double2 cconj(double2 a) { return make_double2(a.x, -a.y); }
+
+// exp(-i pi t / 8), t = 0..7: W^(t * N/8) for M = 2N
+__device__ __forceinline__ double2 w16th(int t) {
+    const double c1 = 0.92387953251128675613, s1 = 0.38268343236508977173, h = 0.70710678118654752440;
+    switch (t) {
+        case 0: return make_double2(1.0, 0.0);
+        case 1: return make_double2(c1, -s1);
+        case 2: return make_double2(h, -h);
+        case 3: return make_double2(s1, -c1);
+        case 4: return make_double2(0.0, -1.0);
+        case 5: return make_double2(-s1, -c1);
+        case 6: return make_double2(-h, -h);
+        default: return make_double2(-c1, -s1);
+    }
+}
+
+template <int LOG2N>
+__global__ void __launch_bounds__(FftLaunch<LOG2N>::THREADS, FftLaunch<LOG2N>::MINB)
+k2_rfft_forward(const FftArgs a, int ngroups_per_member, int ngroups_total) {
+    using L = FftLaunch<LOG2N>;
+    using F = RowFft<LOG2N, -1>;
+    static_assert(L::RPB == 1, "long-row path: one row per CTA");
+    extern __shared__ __align__(16) double2 fft_smem[];
+    constexpr int N = L::N, TPR = L::TPR, M = 2 * N;
+    const int lt = threadIdx.x;
+    double2* s = fft_smem;
+    F fft;
+    fft.init(a.pl.tw, lt, 2);             // half-length twiddles: exp(-2 pi i n / N) = tw[2n]
+    const double2 w0 = __ldg(a.pl.tw + lt);   // W^lt, W = exp(-2 pi i / M)
+
+    for (int grp = blockIdx.x; grp < ngroups_total; grp += gridDim.x) {
+        const int member = grp / ngroups_per_member;
+        const int rf = grp - member * ngroups_per_member;
+        const int row = rf >> 1, field = rf & 1;
+        const double A0 = a.A[2 * field], A1 = a.A[2 * field + 1];   // row `field` of P_inv
+        const double2* __restrict__ q1 = reinterpret_cast<const double2*>(a.q1 + member * a.mstride + a.g.at(0, row));
+        const double2* __restrict__ q2 = reinterpret_cast<const double2*>(a.q2 + member * a.mstride + a.g.at(0, row));
+        double2 v[8];
+#pragma unroll
+        for (int t = 0; t < 8; ++t) {
+            const double2 x1 = __ldg(q1 + lt + t * TPR), x2 = __ldg(q2 + lt + t * TPR);
+            v[t] = make_double2(A0 * x1.x + A1 * x2.x, A0 * x1.y + A1 * x2.y);   // (q~[2n], q~[2n+1])
+        }
+        fft.template run<true>(v, s, lt);
+        double2* __restrict__ out =
+            reinterpret_cast<double2*>(a.S + member * a.sstride + (int64_t)row * a.pl.ncol);
+        double* __restrict__ outs = reinterpret_cast<double*>(out);
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+            const int k = lt + b * TPR;   // 0 .. N/2 - 1
+            if (k == 0) {
+                const double2 Z0 = s[swz(0)], Zh = s[swz(N / 2)];
+                outs[0 + field] = Z0.x + Z0.y;              // X[0]  -> slot 0, component `field`
+                outs[2 * N + field] = Z0.x - Z0.y;          // X[N]  -> slot M/2
+                const double2 Xh = cconj(Zh);               // X[N/2]
+                if (field == 0) out[N / 2] = Xh; else out[M - N / 2] = Xh;
+                if (field == 0) a.col0[(int64_t)member * a.pl.P + row] = Z0.x + Z0.y;
+            } else {
+                const double2 Za = s[swz(k)], Zb = s[swz(N - k)];
+                const double2 E = make_double2(0.5 * (Za.x + Zb.x), 0.5 * (Za.y - Zb.y));
+                const double2 O = make_double2(0.5 * (Za.y + Zb.y), 0.5 * (Zb.x - Za.x));
+                const double2 T = cmul(cmul(w0, w16th(b)), O);   // W^k O, k = lt + b N/8 = lt + b M/16
+                const double2 Xk = cadd(E, T), Xm = cconj(csub(E, T));   // X[k], X[N-k]
+                if (field == 0) { out[k] = Xk; out[N - k] = Xm; }
+                else { out[M - k] = Xk; out[M - N + k] = Xm; }
+            }
+        }
+        __syncthreads();
+    }
+}
+
+template <int LOG2N>
+__global__ void __launch_bounds__(FftLaunch<LOG2N>::THREADS, FftLaunch<LOG2N>::MINB)
+k4_rfft_inverse(const FftArgs a, int ngroups_per_member, int ngroups_total) {
+    using L = FftLaunch<LOG2N>;
+    using F = RowFft<LOG2N, +1>;
+    extern __shared__ __align__(16) double2 fft_smem[];
+    constexpr int N = L::N, TPR = L::TPR, M = 2 * N;
+    const int lt = threadIdx.x;
+    double2* s = fft_smem;
+    F fft;
+    fft.init(a.pl.tw, lt, 2);
+    const double2 w0c = cconj(__ldg(a.pl.tw + lt));   // W^-lt
+    const int P = a.g.P;
+    const int64_t dyo = (int64_t)P * a.g.pitch;
+
+    for (int grp = blockIdx.x; grp < ngroups_total; grp += gridDim.x) {
+        const int member = grp / ngroups_per_member;
+        const int rl = grp - member * ngroups_per_member;
+        const int row = rl >> 1, layer = rl & 1;
+        const double P0 = a.A[2 * layer], P1 = a.A[2 * layer + 1];   // row `layer` of P
+        const double gauge = a.use_gauge ? a.scal[member * 4 + 1] : 0.0;
+        const double2* __restrict__ in =
+            reinterpret_cast<const double2*>(a.S + member * a.sstride + (int64_t)row * a.pl.ncol);
+        double2 v[8];
+#pragma unroll
+        for (int t = 0; t < 8; ++t) {
+            const int k = lt + t * TPR;   // 0 .. N-1
+            if (k == 0) {
+                const double2 s0 = __ldg(in), sN = __ldg(in + N);   // (U1[0], U2[0]), (U1[N], U2[N])
+                const double X0 = P0 * (s0.x - gauge) + P1 * s0.y, XN = P0 * sN.x + P1 * sN.y;
+                v[t] = make_double2(X0 + XN, X0 - XN);
+            } else {
+                // X[k] = P0 U1[k] + P1 U2[k];  U1[k] = slot k, U2[k] = slot M-k
+                const double2 a1 = __ldg(in + k), a2 = __ldg(in + M - k);
+                const double2 b1 = __ldg(in + N - k), b2 = __ldg(in + N + k);
+                const double2 Xk = make_double2(P0 * a1.x + P1 * a2.x, P0 * a1.y + P1 * a2.y);
+                const double2 Xm = make_double2(P0 * b1.x + P1 * b2.x, P0 * b1.y + P1 * b2.y);   // X[N-k]
+                const double2 E = make_double2(Xk.x + Xm.x, Xk.y - Xm.y);                        // X[k] + conj X[N-k]
+                const double2 D = make_double2(Xk.x - Xm.x, Xk.y + Xm.y);                        // X[k] - conj X[N-k]
+                const double2 O = cmul(cmul(w0c, cconj(w16th(t))), D);                           // W^-k (..)
+                v[t] = make_double2(E.x - O.y, E.y + O.x);                                       // E + i O
+            }
+        }
+        fft.template run<false>(v, s, lt);
+        double* __restrict__ p = (layer == 0 ? a.psi1 : a.psi2) + member * a.mstride;
+        const bool gb = a.periodic_y && row < GHOST, gt = a.periodic_y && row >= P - GHOST;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            const int n = F::out_index(lt, e);        // z[n] = (psi[2n], psi[2n+1])
+            const int64_t o = a.g.at(2 * n, row);
+            const double2 z = v[e];
+            *reinterpret_cast<double2*>(p + o) = z;
+            const bool gl = n == 0, gr = n == N - 1;   // columns 0,1 / M-2,M-1 feed the x ghosts
+            if (gl) *reinterpret_cast<double2*>(p + o + M) = z;
+            if (gr) *reinterpret_cast<double2*>(p + o - M) = z;
+            if (gb) {
+                *reinterpret_cast<double2*>(p + o + dyo) = z;
+                if (gl) *reinterpret_cast<double2*>(p + o + dyo + M) = z;
+                if (gr) *reinterpret_cast<double2*>(p + o + dyo - M) = z;
+            }
+            if (gt) {
+                *reinterpret_cast<double2*>(p + o - dyo) = z;
+                if (gl) *reinterpret_cast<double2*>(p + o - dyo + M) = z;
+                if (gr) *reinterpret_cast<double2*>(p + o - dyo - M) = z;
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// ---------------------------------------------------------------------------------------
 // Direct DFT path for M that is not a power of two (or < 8).  One row per block.
 // ---------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
@@ -479,6 +630,28 @@ static cudaError_t launch_pow2(Handle* h, const FftArgs& a) {
     return cudaGetLastError();
 }
 
+template <int LOG2N, bool FWD>
+static cudaError_t launch_long(Handle* h, const FftArgs& a) {
+    using L = FftLaunch<LOG2N>;
+    auto kern = FWD ? k2_rfft_forward<LOG2N> : k4_rfft_inverse<LOG2N>;
+    static bool configured = false;
+    static int blocks_per_sm = 1;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::SMEM);
+        if (e != cudaSuccess) return e;
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, kern, L::THREADS, L::SMEM);
+        if (e != cudaSuccess) return e;
+        if (blocks_per_sm < 1) blocks_per_sm = 1;
+        configured = true;
+    }
+    const int gpm = 2 * h->plan.P;   // (row, field) or (row, layer)
+    const int total = gpm * h->nm;
+    int grid = num_sms() * blocks_per_sm;
+    if (grid > total) grid = total;
+    kern<<<grid, L::THREADS, L::SMEM, h->stream>>>(a, gpm, total);
+    return cudaGetLastError();
+}
+
 template <bool FWD>
 static cudaError_t dispatch_pow2(Handle* h, const FftArgs& a) {
     switch (h->plan.log2M) {
@@ -493,6 +666,7 @@ static cudaError_t dispatch_pow2(Handle* h, const FftArgs& a) {
         case 11: return launch_pow2<11, FWD>(h, a);
         case 12: return launch_pow2<12, FWD>(h, a);
         case 13: return launch_pow2<13, FWD>(h, a);
+        case 14: return launch_long<13, FWD>(h, a);   // M = 16384: half-length real transform
         default: return cudaErrorInvalidValue;
     }
 }

@@ -157,7 +157,7 @@ cudaError_t build_plan(Handle* h) {
     pl.P = P;
     pl.ncol = 2 * M;
     pl.log2M = ilog2_exact(M);
-    pl.pow2 = (pl.log2M >= 3 && M <= 8192) ? 1 : 0;
+    pl.pow2 = (pl.log2M >= 3 && M <= 16384) ? 1 : 0;
     if (pl.pow2) {
         pl.tpr = M / 8;
         pl.rpb = pl.tpr >= 128 ? 1 : 128 / pl.tpr;
@@ -346,7 +346,7 @@ int qg_create(const qg_params* p, int device, int nmembers, void* stream, qg_han
         return fail(nullptr, QG_ERR_INVALID, "qg_create: alpha (S_eig) must be negative (modified Helmholtz)");
     if (p->P > 16384) return fail(nullptr, QG_ERR_INVALID, "qg_create: P > 16384 not supported");
     const bool pow2 = (p->M & (p->M - 1)) == 0 && p->M >= 8;
-    if (pow2 && p->M > 8192) return fail(nullptr, QG_ERR_INVALID, "qg_create: M > 8192 not supported yet");
+    if (pow2 && p->M > 16384) return fail(nullptr, QG_ERR_INVALID, "qg_create: M > 16384 not supported");
     if (!pow2 && p->M > 4096)
         return fail(nullptr, QG_ERR_INVALID, "qg_create: non-power-of-two M > 4096 not supported");
     int ndev = 0;

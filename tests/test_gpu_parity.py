@@ -57,7 +57,7 @@ def test_ten_steps_against_golden(name, golden_dir):
     (8, 8, "direct"), (9, 7, "direct"), (3, 3, "direct"), (4, 5, "direct"), (16, 33, "direct"),
     (40, 24, "direct"), (56, 56, "direct"), (128, 128, "direct"), (128, 100, "spectral"),
     (512, 512, "spectral"), (256, 1100, "spectral"), (1024, 1024, "spectral"), (2048, 96, "spectral"),
-    (8192, 64, "spectral"), (64, 4160, "spectral"),
+    (8192, 64, "spectral"), (64, 4160, "spectral"), (16384, 64, "spectral"),
 ])
 def test_ten_steps_against_oracle(M, P, backend):
     """psi, q (and the RHS history) after 10 steps; covers power-of-two and general M,
@@ -231,3 +231,21 @@ def test_error_reporting():
             s.evolve_zeta(0)   # timestep is 1-based
         with pytest.raises(ValueError):
             s.upload(np.zeros((16, 16, 2, 3)), None, None)
+
+
+def test_y_slab_decomposition_on_two_gpus():
+    """One run split into y-slabs over 2 GPUs (NCCL halo ring + carry all-gather) equals the
+    oracle's global solution; needs two visible GPUs, launched as one process per GPU."""
+    import os
+    import subprocess
+    import sys
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    for M, P in ((256, 256), (512, 1024)):
+        out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                              "--master-addr", "127.0.0.1", "--master-port", "29541",
+                              os.path.join(root, "tests", "dist_slab_check.py"), str(M), str(P), "10"],
+                             capture_output=True, text=True, timeout=600)
+        assert "SLAB_CHECK_OK" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]

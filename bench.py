@@ -135,6 +135,77 @@ def run_reference(args, rank, world):
     print(json.dumps(line), flush=True)
 
 
+def run_slab(args, rank, world, local_rank, torch, dist, qgb200, np):
+    """BASELINE.json config 4: one run split into y-slabs over the GPUs of the node (NCCL halo
+    ring + carry all-gather).  value = global cells x steps / max-over-ranks device time."""
+    M, P = args.grid
+    a = model_args(M, P)
+    glob = qgb200.BaroclinicModel(*[a[k] for k in ("H_1", "H_2", "beta", "Lx", "Ly", "dt", "T", "U", "M", "P", "dx",
+                                                   "visc", "r", "R_d", "initial_kick")])
+    model = qgb200.slab.local_model(glob, world)
+    K, W = args.steps, max(args.warmup, 3)
+    # per-rank seeded slab: psi noise, q from the slab-periodic Laplacian (throughput does not depend on it)
+    zeta, psi = qgb200.initialise_model(model, seed=1 + rank)
+    f = np.zeros_like(zeta)
+    ids = [qgb200.Session.nccl_unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(ids, src=0)
+    stream = torch.cuda.Stream()
+    torch.cuda.set_stream(stream)
+    sess = qgb200.Session(model, members=1, device=local_rank, stream=stream.cuda_stream)
+    sess.dist_init(rank, world, ids[0])
+    sess.upload(zeta, psi, f)
+    del zeta, psi, f
+    sess.step(1, W)
+    torch.cuda.synchronize(); dist.barrier(); torch.cuda.synchronize()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    sess.set_profiling(True)
+    l0 = sess.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    sess.step(W + 1, K)
+    e1.record(stream)
+    torch.cuda.synchronize(); dist.barrier(); torch.cuda.synchronize()
+    ms_total = e0.elapsed_time(e1)
+    launches = sess.launch_count() - l0
+    ktimes = sess.kernel_times()
+    sess.set_profiling(False)
+    sampler.stop_flag = True
+    sampler.join(timeout=2.0)
+    E, Z = sess.diagnostics()
+    tmax = torch.tensor([ms_total], dtype=torch.float64, device="cuda")
+    dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+    ms_total = float(tmax[0])
+    sess.close()
+    if rank == 0:
+        cells = float(M) * P
+        value = cells * K / (ms_total * 1e-3)
+        peak, peak_src = peaks()
+        per = {k: (ms / n * 1e-3 if n else 0.0) for k, (ms, n) in ktimes.items()}
+        local_cells = cells / world
+        kern = {k: {"us": round(per[k] * 1e6, 2)} for k in per if per[k]}
+        dom = "k1_zeta_step"
+        ach = KERNEL_BYTES[dom] * local_cells / per[dom] / 1e9
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+                "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+                "dtype": "f64", "data": "synthetic",
+                "config": {"workload": f"Phillips two-layer {M}x{P}, Float64, ONE run in {world} y-slabs of "
+                                       f"{P // world} rows (BASELINE.json config 4): NCCL send/recv halo ring, "
+                                       f"all-gather of the y-solve carries in place of the all-to-all transpose",
+                           "dt_s": a["dt"], "parallelism": f"y-slab x{world}",
+                           "ic": "per-rank seeded slab (psi noise, q from the slab-periodic Laplacian)"},
+                "roofline": {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s",
+                             "frac": ach / peak, "traffic": None, "peak_source": peak_src,
+                             "per_rank_kernels_us": kern,
+                             "step": {"achieved_per_gpu": STEP_BYTES * local_cells * K / (ms_total * 1e-3) / 1e9,
+                                      "frac": STEP_BYTES * local_cells * K / (ms_total * 1e-3) / 1e9 / peak}},
+                "e2e": None, "gpu_launches": int(launches), "clocks": sampler.result(),
+                "diagnostics": {"E": float(E), "Z": float(Z)}}
+        print(json.dumps(line), flush=True)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -143,6 +214,9 @@ def main():
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--grid", type=int, nargs=2, default=[4096, 4096])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--mode", default="ensemble", choices=["ensemble", "slab"],
+                    help="N > 1: 'ensemble' = one independent run per GPU (default, weak scaling); "
+                         "'slab' = ONE run of --grid split into y-slabs over the GPUs (strong scaling)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -163,6 +237,8 @@ def main():
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    if args.mode == "slab" and world > 1:
+        return run_slab(args, rank, world, local_rank, torch, dist, qgb200, np)
     M, P = args.grid
     a = model_args(M, P)
     model = qgb200.BaroclinicModel(*[a[k] for k in ("H_1", "H_2", "beta", "Lx", "Ly", "dt", "T", "U", "M", "P", "dx",

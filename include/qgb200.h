@@ -91,6 +91,12 @@ int qg_destroy(qg_handle* h);
  * zeros). */
 int qg_upload_state(qg_handle* h, const double* zeta, const double* psi, const double* f_store);
 
+/* Same, for the state a run starts from: only time level 1 of zeta and psi is read from the
+ * host arrays (same (M+2, P+2, 2, 3) layout); levels 2-3 and f_store are zeroed on the device,
+ * which is exactly what initialise_model (src/model.jl:53-59) and
+ * src/run_model_no_output.jl:8 hand to the loop.  Moves 4.5x fewer bytes over PCIe. */
+int qg_upload_initial_state(qg_handle* h, const double* zeta, const double* psi);
+
 /* Device -> host, all three time levels, ghosts included, reference layout.  Any pointer
  * may be NULL. */
 int qg_download_state(qg_handle* h, double* zeta, double* psi, double* f_store);

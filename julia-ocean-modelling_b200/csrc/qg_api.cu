@@ -402,6 +402,7 @@ int qg_create(const qg_params* p, int device, int nmembers, void* stream, qg_han
     h->diag_blocks = p->P < 592 ? p->P : 592;
     QG_TRY(cudaMalloc((void**)&h->diag_part, ((size_t)nmembers * h->diag_blocks * 2 + 2 * nmembers) * sizeof(double)));
     QG_TRY(build_plan(h));
+    if (getenv("QG_NO_GRAPH")) h->use_graph = false;
     {
         const char* ty = getenv("QG_K1_TY");
         const int v = ty ? atoi(ty) : (p->P >= 512 ? 24 : 16);   // measured on B200: 24 rows is best at 4096^2
@@ -427,6 +428,9 @@ int qg_destroy(qg_handle* h) {
     cudaFree(h->q); cudaFree(h->psi); cudaFree(h->f); cudaFree(h->S); cudaFree(h->k0sol);
     cudaFree(h->scal); cudaFree(h->stage); cudaFree(h->diag_part);
     for (cudaEvent_t e : h->evpool) cudaEventDestroy(e);
+    for (int a = 0; a < 3; ++a)
+        for (int b = 0; b < 3; ++b)
+            if (h->gexec[a][b]) cudaGraphExecDestroy(h->gexec[a][b]);
     if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
     delete h;
     return QG_OK;
@@ -493,6 +497,38 @@ int qg_upload_state(qg_handle* h, const double* zeta, const double* psi, const d
     return QG_OK;
 }
 
+// level 1 of one array only (2 fields per member), the other levels zeroed
+static int upload_level1(qg_handle* h, const double* host, double* dev) {
+    const size_t hs = (size_t)(h->g.M + 2) * (h->g.P + 2);
+    QG_CUDA(h, cudaMemsetAsync(dev, 0, (size_t)h->nfields * h->g.fstride * sizeof(double), h->stream));
+    for (int m = 0; m < h->nm; ++m)
+        QG_CUDA(h, cudaMemcpyAsync(h->stage + (size_t)m * 6 * hs, host + (size_t)m * 6 * hs, 2 * hs * sizeof(double),
+                                   cudaMemcpyHostToDevice, h->stream));
+    dim3 block(128), grid((h->g.M + 2 * GHOST + 127) / 128, h->g.P + 2 * GHOST, h->nm * 2);
+    {
+        KernelTimer t(h, QG_K_PACK);
+        k_unpack<<<grid, block, 0, h->stream>>>(h->stage, dev, h->g, h->nm, 0, 2, 1);
+    }
+    QG_CUDA(h, cudaGetLastError());
+    if (h->dist_n > 1) QG_CUDA(h, dist_halo_exchange(h, dev, 0));
+    return QG_OK;
+}
+
+int qg_upload_initial_state(qg_handle* h, const double* zeta, const double* psi) {
+    if (!h || !zeta || !psi) return QG_ERR_INVALID;
+    QG_CUDA(h, cudaSetDevice(h->device));
+    int rc = ensure_stage(h);
+    if (rc) return rc;
+    h->qcur = 0;
+    h->pcur = 0;
+    if ((rc = upload_level1(h, zeta, h->q))) return rc;
+    if ((rc = upload_level1(h, psi, h->psi))) return rc;
+    QG_CUDA(h, cudaMemsetAsync(h->f, 0, (size_t)h->nfields * h->g.fstride * sizeof(double), h->stream));
+    QG_CUDA(h, cudaStreamSynchronize(h->stream));
+    h->have_state = true;
+    return QG_OK;
+}
+
 int qg_download_state(qg_handle* h, double* zeta, double* psi, double* f_store) {
     if (!h) return QG_ERR_INVALID;
     if (!h->have_state) return fail(h, QG_ERR_STATE, "qg_download_state: no state uploaded");
@@ -520,16 +556,72 @@ int qg_evolve_psi(qg_handle* h) {
     return do_evolve_psi(h);
 }
 
+// Replay (capturing on first use) the 3-step AB3 cycle that starts from the current slot phase.
+static int step_cycle_graph(qg_handle* h, int t) {
+    const int a = h->qcur, b = h->pcur;
+    if (!h->gexec[a][b]) {
+        const int64_t l0 = h->launches;
+        int64_t k0[QG_NKERNELS];
+        for (int i = 0; i < QG_NKERNELS; ++i) k0[i] = h->kcount[i];
+        cudaGraph_t graph = nullptr;
+        if (cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal) != cudaSuccess) {
+            cudaGetLastError();
+            h->use_graph = false;
+            return 1;
+        }
+        int rc = QG_OK;
+        for (int i = 0; i < 3 && rc == QG_OK; ++i) {
+            rc = do_evolve_zeta(h, t + i);
+            if (rc == QG_OK) rc = do_evolve_psi(h);
+        }
+        cudaError_t e = cudaStreamEndCapture(h->stream, &graph);
+        if (rc != QG_OK || e != cudaSuccess || !graph ||
+            cudaGraphInstantiate(&h->gexec[a][b], graph, 0) != cudaSuccess) {
+            cudaGetLastError();
+            if (graph) cudaGraphDestroy(graph);
+            h->gexec[a][b] = nullptr;
+            h->use_graph = false;
+            h->qcur = a;
+            h->pcur = b;
+            h->launches = l0;
+            for (int i = 0; i < QG_NKERNELS; ++i) h->kcount[i] = k0[i];
+            return 1;   // caller falls back to plain launches
+        }
+        cudaGraphDestroy(graph);
+        h->glaunches[a][b] = h->launches - l0;
+        for (int i = 0; i < QG_NKERNELS; ++i) h->gkcount[a][b][i] = h->kcount[i] - k0[i];
+        // capture only recorded the work: undo the bookkeeping, the launch below redoes it
+        h->launches = l0;
+        for (int i = 0; i < QG_NKERNELS; ++i) h->kcount[i] = k0[i];
+    }
+    QG_CUDA(h, cudaGraphLaunch(h->gexec[a][b], h->stream));
+    h->launches += h->glaunches[a][b];
+    for (int i = 0; i < QG_NKERNELS; ++i) h->kcount[i] += h->gkcount[a][b][i];
+    // three steps rotate every slot back: qcur and pcur are unchanged
+    h->qcur = a;
+    h->pcur = b;
+    return QG_OK;
+}
+
 int qg_step(qg_handle* h, int first_timestep, int nsteps) {
     if (!h) return QG_ERR_INVALID;
     if (!h->have_state) return fail(h, QG_ERR_STATE, "qg_step: no state uploaded");
     if (first_timestep < 1 || nsteps < 0) return fail(h, QG_ERR_INVALID, "qg_step: bad timestep range");
     QG_CUDA(h, cudaSetDevice(h->device));
-    for (int t = first_timestep; t < first_timestep + nsteps; ++t) {
+    const int end = first_timestep + nsteps;
+    int t = first_timestep;
+    while (t < end) {
+        if (h->use_graph && h->warm && !h->profiling && h->dist_n == 1 && t >= 3 && end - t >= 3) {
+            const int rc = step_cycle_graph(h, t);
+            if (rc == QG_OK) { t += 3; continue; }
+            if (rc < 0) return rc;
+        }
         int rc = do_evolve_zeta(h, t);
         if (rc) return rc;
         rc = do_evolve_psi(h);
         if (rc) return rc;
+        h->warm = true;
+        ++t;
     }
     return QG_OK;
 }

@@ -168,6 +168,13 @@ struct Handle {
     int diag_blocks = 0;
     int64_t launches = 0;
     int profiling = 0;
+    // CUDA graphs of the steady state: three AB3 steps return every rotating slot to where it
+    // started, so one captured 3-step cycle per (qcur, pcur) phase replays for the rest of the run
+    cudaGraphExec_t gexec[3][3] = {};
+    int64_t glaunches[3][3] = {};       // kernel launches inside each graph
+    int64_t gkcount[3][3][QG_NKERNELS] = {};
+    bool use_graph = true;
+    bool warm = false;
     std::vector<cudaEvent_t> evpool;   // start/stop pairs
     std::vector<int> evkernel;         // kernel id of each recorded pair
     int ev_next(int id) {

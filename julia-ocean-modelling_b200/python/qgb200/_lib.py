@@ -40,6 +40,7 @@ SYMBOLS = {
     "qg_create": (C.c_int, [C.POINTER(qg_params), C.c_int, C.c_int, _P, C.POINTER(_P)]),
     "qg_destroy": (C.c_int, [_P]),
     "qg_upload_state": (C.c_int, [_P, _P, _P, _P]),
+    "qg_upload_initial_state": (C.c_int, [_P, _P, _P]),
     "qg_download_state": (C.c_int, [_P, _P, _P, _P]),
     "qg_evolve_zeta": (C.c_int, [_P, C.c_int]),
     "qg_evolve_psi": (C.c_int, [_P]),

@@ -216,6 +216,16 @@ class Session:
                 _as_state(a, self.model, self.members, name)
         self._ck(self._lib.qg_upload_state(self._h, self._ptr(zeta), self._ptr(psi), self._ptr(f_store)))
 
+    def upload_initial(self, zeta, psi):
+        """Level 1 of zeta and psi only; history levels and f_store are zeroed on the device
+        (the state initialise_model produces)."""
+        for name, a in (("zeta", zeta), ("psi", psi)):
+            _as_state(a, self.model, self.members, name)
+        self._ck(self._lib.qg_upload_initial_state(self._h, self._ptr(zeta), self._ptr(psi)))
+
+    def upload_initial_raw(self, zeta_ptr, psi_ptr):
+        self._ck(self._lib.qg_upload_initial_state(self._h, C.c_void_p(zeta_ptr), C.c_void_p(psi_ptr)))
+
     def download(self, zeta=None, psi=None, f_store=None):
         for name, a in (("zeta", zeta), ("psi", psi), ("f_store", f_store)):
             if a is not None:
@@ -402,9 +412,8 @@ def run_model_no_output(model, seed=None, rand_fields=None, device=0, total_step
     get_helmholtz_cholesky(model.M, model.P, model.dx, S_eig(model))
     if total_steps is None:
         total_steps = int(np.floor(model.T / model.dt))
-    f_store = np.zeros((model.M + 2, model.P + 2, 2, 3), order="F")
     with Session(model, 1, device) as s:
-        s.upload(zeta, psi, f_store)
+        s.upload_initial(zeta, psi)      # f_store = zeros (src/run_model_no_output.jl:8) on the device
         s.step(1, total_steps)
         s.download(zeta=zeta, psi=psi)
     return zeta, psi

@@ -205,6 +205,16 @@ struct RowFft {
     }
 };
 
+// psi~1(0,0) of one member: the fixed-order sum of K3's per-slab shares (or the value k3_gauge
+// left in scal[1]).  Called by every thread of the block; two block barriers.
+__device__ __forceinline__ double load_gauge(const FftArgs& a, int member, double* sh) {
+    if (!a.use_gauge) return 0.0;
+    if (a.gpart == nullptr) return a.scal[member * 4 + 1];
+    double loc = 0.0;
+    for (int i = threadIdx.x; i < a.ngp; i += blockDim.x) loc += a.gpart[(int64_t)member * a.ngp + i];
+    return block_sum(loc, sh);
+}
+
 template <int LOG2N>
 struct FftLaunch {
     static constexpr int N = 1 << LOG2N;
@@ -289,11 +299,18 @@ k4_fft_inverse(const FftArgs a, int ngroups_per_member, int ngroups_total) {
     const int M = a.g.M, P = a.g.P;
     const int64_t dyo = (int64_t)P * a.g.pitch;
     constexpr int half = N >> 1;
+    __shared__ double gsh[32];
+    int gmember = -1;
+    double gauge = 0.0;
 
     for (int grp = blockIdx.x; grp < ngroups_total; grp += gridDim.x) {
         const int member = grp / ngroups_per_member;
         const int row = (grp - member * ngroups_per_member) * L::RPB + lr;
         const bool live = row < P;
+        if (member != gmember) {   // block-uniform
+            gauge = load_gauge(a, member, gsh);
+            gmember = member;
+        }
         const double2* __restrict__ in =
             reinterpret_cast<const double2*>(a.S + member * a.sstride + (int64_t)(live ? row : 0) * a.pl.ncol);
         // Z[k] = U1[k] + i U2[k] (k < N/2), Z[N-k] = conj(U1[k]) + i conj(U2[k]); slot k holds
@@ -313,7 +330,6 @@ k4_fft_inverse(const FftArgs a, int ngroups_per_member, int ngroups_total) {
         }
         fft.template run<false>(v, s, lt);
         if (live) {
-            const double gauge = a.use_gauge ? a.scal[member * 4 + 1] : 0.0;
             double* __restrict__ p1 = a.psi1 + member * a.mstride;
             double* __restrict__ p2 = a.psi2 + member * a.mstride;
             const bool gb = a.periodic_y && row < GHOST, gt = a.periodic_y && row >= P - GHOST;
@@ -439,13 +455,19 @@ k4_rfft_inverse(const FftArgs a, int ngroups_per_member, int ngroups_total) {
     const double2 w0c = cconj(__ldg(a.pl.tw + lt));   // W^-lt
     const int P = a.g.P;
     const int64_t dyo = (int64_t)P * a.g.pitch;
+    __shared__ double gsh[32];
+    int gmember = -1;
+    double gauge = 0.0;
 
     for (int grp = blockIdx.x; grp < ngroups_total; grp += gridDim.x) {
         const int member = grp / ngroups_per_member;
         const int rl = grp - member * ngroups_per_member;
         const int row = rl >> 1, layer = rl & 1;
         const double P0 = a.A[2 * layer], P1 = a.A[2 * layer + 1];   // row `layer` of P
-        const double gauge = a.use_gauge ? a.scal[member * 4 + 1] : 0.0;
+        if (member != gmember) {
+            gauge = load_gauge(a, member, gsh);
+            gmember = member;
+        }
         const double2* __restrict__ in =
             reinterpret_cast<const double2*>(a.S + member * a.sstride + (int64_t)row * a.pl.ncol);
         double2 v[8];
@@ -564,7 +586,8 @@ k4_dft_inverse(const FftArgs a) {
         z[n] = acc;
     }
     __syncthreads();
-    const double gauge = a.use_gauge ? a.scal[member * 4 + 1] : 0.0;
+    __shared__ double gsh[32];
+    const double gauge = load_gauge(a, member, gsh);
     double* __restrict__ p1 = a.psi1 + member * a.mstride;
     double* __restrict__ p2 = a.psi2 + member * a.mstride;
     const int M = a.g.M, P = a.g.P;
@@ -712,6 +735,10 @@ cudaError_t launch_fft_inverse(Handle* h, double* psi_fields, int use_gauge) {
     a.scal = h->scal;
     a.use_gauge = use_gauge;
     a.periodic_y = h->dist_n > 1 ? 0 : 1;
+    if (h->plan.ts_ok && h->dist_n == 1) {   // K3 left per-slab shares of the gauge instead of running k3_gauge
+        a.gpart = h->gpart;
+        a.ngp = h->plan.ngp;
+    }
     KernelTimer t(h, QG_K_FFT_INV);
     if (h->plan.pow2) return dispatch_pow2<false>(h, a);
     const size_t smem = 2 * (size_t)h->plan.M * sizeof(double2);

@@ -35,9 +35,10 @@ namespace qg {
 constexpr int CH = 32;   // rows per chunk
 
 constexpr int PRE_T = 1024;
-constexpr int PRE_E = 16;   // rows per thread, P <= 16384
 
 // One block per member: statistics and singular solve of the Poisson k=0 column (column 0).
+// PRE_E = rows per thread (P <= 1024 * PRE_E).
+template <int PRE_E>
 __global__ void __launch_bounds__(PRE_T) k3_pre(const YArgs a) {
     __shared__ double sh[32];
     const int member = blockIdx.x;
@@ -95,6 +96,15 @@ __global__ void __launch_bounds__(PRE_T) k3_pre(const YArgs a) {
         if (i < e && j < P) out[j] = xs[i] + off2;
     }
     if (threadIdx.x == 0) a.scal[member * 4 + 0] = pin;
+}
+
+static void launch_pre(const YArgs& a, int nblocks, cudaStream_t st) {
+    const int e = (a.preP + PRE_T - 1) / PRE_T;
+    if (e <= 1) k3_pre<1><<<nblocks, PRE_T, 0, st>>>(a);
+    else if (e <= 2) k3_pre<2><<<nblocks, PRE_T, 0, st>>>(a);
+    else if (e <= 4) k3_pre<4><<<nblocks, PRE_T, 0, st>>>(a);
+    else if (e <= 8) k3_pre<8><<<nblocks, PRE_T, 0, st>>>(a);
+    else k3_pre<16><<<nblocks, PRE_T, 0, st>>>(a);
 }
 
 // One block per member: psi~1 at node (0,0) = sum over all x wavenumbers of row 0 of the
@@ -329,6 +339,7 @@ __global__ void __launch_bounds__(512) k3_ysolve(const YArgs a) {
 constexpr int TS_WC = 16;
 constexpr int TS_LD = 17;   // padded leading dimension of the per-chunk carry arrays
 
+template <int MODE>   // 0: cyclic over the local rows; 1 / 2: y-slab mode, see YArgs::mode
 __global__ void __launch_bounds__(256, 3)
 k3_ysolve_tma(const __grid_constant__ CUtensorMap tmS, const YArgs a, int nchunk) {
     extern __shared__ __align__(128) unsigned char ts_raw[];
@@ -453,7 +464,7 @@ k3_ysolve_tma(const __grid_constant__ CUtensorMap tmS, const YArgs a, int nchunk
             FFi[i] = i < CS ? cluster.map_shared_rank(sFF, i)[cl] : 0.0;
             RRi[i] = i < CS ? cluster.map_shared_rank(sRR, i)[cl] : 1.0;
         }
-        if (a.mode == 1) {
+        if (MODE == 1) {
             // y-slab mode, first kernel: fold the cluster's CTAs into one rank-level aggregate
             // (same affine composition one level up) and stop; the ranks exchange these.
             double t = 0.0, R = 1.0, X = 0.0, Y = 0.0;
@@ -478,7 +489,7 @@ k3_ysolve_tma(const __grid_constant__ CUtensorMap tmS, const YArgs a, int nchunk
 #pragma unroll
         for (int i = 0; i < 8; ++i) tt = fma(RRi[i], tt, FFi[i]);
         // carry into chunk 0: cyclic closure (y at the last row), or handed in by the rank below
-        double as = a.mode == 2 ? __ldg(a.Ain + gc) : tt * inv1;
+        double as = MODE == 2 ? __ldg(a.Ain + gc) : tt * inv1;
         double a_s = 0.0;
         double GGp[8];
 #pragma unroll
@@ -493,7 +504,7 @@ k3_ysolve_tma(const __grid_constant__ CUtensorMap tmS, const YArgs a, int nchunk
 #pragma unroll
         for (int i = 7; i >= 0; --i) tt = fma(RRi[i], tt, GGp[i]);
         // carry into the last chunk: cyclic closure (z at row 0), or handed in by the rank above
-        double b_e = a.mode == 2 ? __ldg(a.Bin + gc) : tt * inv1;
+        double b_e = MODE == 2 ? __ldg(a.Bin + gc) : tt * inv1;
 #pragma unroll
         for (int i = 7; i > 0; --i)
             if (i > cr) b_e = fma(RRi[i], b_e, GGp[i]);
@@ -525,7 +536,7 @@ k3_ysolve_tma(const __grid_constant__ CUtensorMap tmS, const YArgs a, int nchunk
         }
     }
     cluster.barrier_arrive();   // remote reads are done; matched by barrier_wait() before exit
-    if (a.mode == 1) {
+    if (MODE == 1) {
         cluster.barrier_wait();
         return;
     }
@@ -536,7 +547,7 @@ k3_ysolve_tma(const __grid_constant__ CUtensorMap tmS, const YArgs a, int nchunk
         const double A = mine ? sF[chunk * TS_LD + l] : 0.0, B = mine ? sG[chunk * TS_LD + l] : 0.0;
         const double* __restrict__ k0 = a.k0sol + (int64_t)member * a.preP + a.row0;
         double* __restrict__ out = a.S + member * a.sstride + (int64_t)j0 * ncol + ccol;
-        double z = B;
+        double z = B, v0 = 0.0;
 #pragma unroll 4
         for (int i = len - 1; i >= 0; --i) {
             const double y = fma(pw[i * TS_WC + l], A, t[i * TS_WC]);
@@ -544,6 +555,15 @@ k3_ysolve_tma(const __grid_constant__ CUtensorMap tmS, const YArgs a, int nchunk
             double v = kap * z;
             if (col == 0) v = k0[j0 + i];
             if (cvalid) out[(int64_t)i * ncol] = v;
+            v0 = v;   // after the loop: the value at the chunk's first row
+        }
+        // psi~1 at node (0,0) = sum over the x wavenumbers of row 0 of the solved Poisson field:
+        // the half-warp that owns global row 0 leaves this slab's share for K4 to add up
+        if (a.gpart != nullptr && a.row0 + j0 == 0 && len > 0) {   // uniform over the half-warp
+            double g = cvalid ? __ldg(a.pl.gw + ccol) * v0 : 0.0;
+#pragma unroll
+            for (int d = 8; d > 0; d >>= 1) g += __shfl_xor_sync(0xffffu << (tid & 16), g, d, 16);
+            if (l == 0) a.gpart[(int64_t)member * a.ngp + slab] = g;
         }
     }
     cluster.barrier_wait();   // distributed shared memory must outlive every remote read
@@ -606,15 +626,16 @@ static cudaError_t launch_tma_kernel(Handle* h, const YArgs& a) {
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    static size_t configured = 0;
-    if (cfg.dynamicSmemBytes > configured) {
-        cudaError_t e = cudaFuncSetAttribute(k3_ysolve_tma, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    static size_t configured[3] = {0, 0, 0};
+    auto kern = a.mode == 1 ? k3_ysolve_tma<1> : (a.mode == 2 ? k3_ysolve_tma<2> : k3_ysolve_tma<0>);
+    if (cfg.dynamicSmemBytes > configured[a.mode]) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              (int)cfg.dynamicSmemBytes);
         if (e != cudaSuccess) return e;
-        configured = cfg.dynamicSmemBytes;
+        configured[a.mode] = cfg.dynamicSmemBytes;
     }
     KernelTimer t(h, QG_K_YSOLVE);
-    return cudaLaunchKernelEx(&cfg, k3_ysolve_tma, h->tm_S, a, pl.ts_nchunk);
+    return cudaLaunchKernelEx(&cfg, kern, h->tm_S, a, pl.ts_nchunk);
 }
 
 // y-slab mode: gather the k=0 column, solve it redundantly on every rank, sweep + exchange the
@@ -637,7 +658,7 @@ static cudaError_t launch_ysolve_dist(Handle* h, int pinned) {
     if (e != cudaSuccess) return e;
     {
         KernelTimer t(h, QG_K_YPRE);
-        k3_pre<<<1, PRE_T, 0, h->stream>>>(a);
+        launch_pre(a, 1, h->stream);
     }
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
     a.mode = 1;
@@ -671,9 +692,13 @@ cudaError_t launch_ysolve(Handle* h, int pinned, int /*unused*/) {
     a.pinned = pinned;
     a.col0 = h->col0;
     a.preP = h->plan.P;
+    if (h->plan.ts_ok) {   // the gauge is assembled from per-slab partial sums (no extra kernel)
+        a.gpart = h->gpart;
+        a.ngp = h->plan.ngp;
+    }
     {
         KernelTimer t(h, QG_K_YPRE);
-        k3_pre<<<h->nm, PRE_T, 0, h->stream>>>(a);
+        launch_pre(a, h->nm, h->stream);
     }
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
@@ -708,7 +733,7 @@ cudaError_t launch_ysolve(Handle* h, int pinned, int /*unused*/) {
         }
     }
     if (e != cudaSuccess) return e;
-    {
+    if (!h->plan.ts_ok) {
         KernelTimer t(h, QG_K_GAUGE);
         k3_gauge<<<h->nm, 256, 0, h->stream>>>(a);
     }

@@ -190,7 +190,7 @@ cudaError_t build_plan(Handle* h) {
     const long double PI = 3.14159265358979323846264338327950288L;
     const long double dx2 = (long double)h->prm.dx * (long double)h->prm.dx;
     std::vector<double> rtab(pl.ncol), kap(pl.ncol), rho32(pl.ncol), h32(pl.ncol), rhoL(pl.ncol),
-        hL(pl.ncol), inv1(pl.ncol), pinw(pl.ncol);
+        hL(pl.ncol), inv1(pl.ncol), pinw(pl.ncol), gw(pl.ncol);
     for (int col = 0; col < pl.ncol; ++col) {
         const int s = col >> 1, part = col & 1;
         int field, k;
@@ -216,6 +216,8 @@ cudaError_t build_plan(Handle* h) {
         inv1[col] = singular ? 1.0 : (double)(1.0L / (1.0L - rP));
         const bool is_re = (s == 0 || ((M % 2 == 0) && s == M / 2)) ? true : (part == 0);
         pinw[col] = (field == 0 && is_re) ? 1.0 : 0.0;
+        // weight of this column in psi~1(0,0) = sum_k U1[k] over all M wavenumbers (Hermitian pairs count twice)
+        gw[col] = (field == 0 && is_re) ? ((k == 0 || 2 * k == M) ? 1.0 : 2.0) : 0.0;
     }
     cudaError_t e;
     if ((e = upload_vec(&pl.tw, tw)) != cudaSuccess) return e;
@@ -227,6 +229,8 @@ cudaError_t build_plan(Handle* h) {
     if ((e = upload_vec(&pl.hL, hL)) != cudaSuccess) return e;
     if ((e = upload_vec(&pl.inv1mrP, inv1)) != cudaSuccess) return e;
     if ((e = upload_vec(&pl.pinw, pinw)) != cudaSuccess) return e;
+    if ((e = upload_vec(&pl.gw, gw)) != cudaSuccess) return e;
+    pl.ngp = (pl.ncol + 15) / 16;
     h->plan_ok = true;
     return cudaSuccess;
 }
@@ -234,7 +238,7 @@ cudaError_t build_plan(Handle* h) {
 void free_plan(Handle* h) {
     Plan& pl = h->plan;
     cudaFree(pl.tw); cudaFree(pl.rtab); cudaFree(pl.kap); cudaFree(pl.rho32); cudaFree(pl.h32);
-    cudaFree(pl.rhoL); cudaFree(pl.hL); cudaFree(pl.inv1mrP); cudaFree(pl.pinw);
+    cudaFree(pl.rhoL); cudaFree(pl.hL); cudaFree(pl.inv1mrP); cudaFree(pl.pinw); cudaFree(pl.gw);
     memset(&pl, 0, sizeof(pl));
     h->plan_ok = false;
 }
@@ -396,6 +400,7 @@ int qg_create(const qg_params* p, int device, int nmembers, void* stream, qg_han
     QG_TRY(cudaMalloc((void**)&h->S, (size_t)nmembers * p->P * 2 * p->M * sizeof(double)));
     QG_TRY(cudaMalloc((void**)&h->k0sol, (size_t)nmembers * p->P * sizeof(double)));
     QG_TRY(cudaMalloc((void**)&h->col0, (size_t)nmembers * p->P * sizeof(double)));
+    QG_TRY(cudaMalloc((void**)&h->gpart, (size_t)nmembers * ((2 * p->M + 15) / 16) * sizeof(double)));
     h->Pglob = p->P;
     QG_TRY(cudaMalloc((void**)&h->scal, (size_t)nmembers * 4 * sizeof(double)));
     QG_TRY(cudaMemsetAsync(h->scal, 0, (size_t)nmembers * 4 * sizeof(double), h->stream));
@@ -425,6 +430,7 @@ int qg_destroy(qg_handle* h) {
     dist_destroy(h);
     free_plan(h);
     cudaFree(h->col0);
+    cudaFree(h->gpart);
     cudaFree(h->q); cudaFree(h->psi); cudaFree(h->f); cudaFree(h->S); cudaFree(h->k0sol);
     cudaFree(h->scal); cudaFree(h->stage); cudaFree(h->diag_part);
     for (cudaEvent_t e : h->evpool) cudaEventDestroy(e);

@@ -69,7 +69,8 @@ struct Plan {
     int wpc, CS, m;          // warps per CTA, cluster size, chunks per warp (register variant)
     int ts_ok, ts_CS, ts_nchunk;   // TMA-staged variant: usable, cluster size, chunks per CTA
     double2* tw;             // exp(-2 pi i n / M), n < M
-    double *rtab, *kap, *rho32, *h32, *rhoL, *hL, *inv1mrP, *pinw;   // per real column
+    double *rtab, *kap, *rho32, *h32, *rhoL, *hL, *inv1mrP, *pinw, *gw;   // per real column
+    int ngp;                 // gauge partial sums per member (= slabs of the TMA y-solve)
     double k0scale;          // dx^2 / M
 };
 
@@ -87,6 +88,8 @@ struct FftArgs {
     const double* scal;  // per member: [0] = sum of the Poisson k=0 column, [1] = gauge
     int use_gauge;
     int periodic_y;      // 1: write the y ghost images locally; 0: y-slab mode (halo exchange fills them)
+    const double* gpart; // inverse: per-slab shares of the gauge (ngp per member), or nullptr -> scal[1]
+    int ngp;
     double* col0;        // forward: compact copy of the Poisson k=0 column, [member * P + row]
 };
 
@@ -107,6 +110,8 @@ struct YArgs {
     // backward carry into the last local row).  mode 0 = cyclic over the local rows.
     int mode;
     double* aggr;       // [4][ncol]
+    double* gpart;      // [member][ngp] per-slab shares of psi~1(0,0); nullptr: k3_gauge -> scal[1]
+    int ngp;
     const double* Ain;  // [ncol]
     const double* Bin;  // [ncol]
 };
@@ -155,6 +160,7 @@ struct Handle {
     double* scal = nullptr;          // [nm][4]
     double* stage = nullptr;         // host-layout staging (3*2*(M+2)*(P+2)*nm doubles)
     double* col0 = nullptr;          // [nm][P] compact Poisson k=0 column (written by K2)
+    double* gpart = nullptr;         // [nm][ngp] gauge partial sums (written by K3, summed by K4)
     // ---- y-slab decomposition of one run over several GPUs (qg_dist_init) ----
     int dist_n = 1, dist_rank = 0;
     int Pglob = 0;                   // global row count (= P when not distributed)

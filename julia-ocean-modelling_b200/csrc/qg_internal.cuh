@@ -280,21 +280,20 @@ __device__ __forceinline__ double warp_sum(double v) {
     return v;
 }
 
-// deterministic block sum, result broadcast to all threads
+// deterministic block sum, result broadcast to all threads (every warp reduces the same
+// per-warp totals in the same order)
 __device__ __forceinline__ double block_sum(double v, double* sh) {
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
     v = warp_sum(v);
     __syncthreads();
     if (lane == 0) sh[w] = v;
     __syncthreads();
-    double t = 0.0;
-    for (int i = 0; i < nw; ++i) t += sh[i];
-    return t;
+    return warp_sum(lane < nw ? sh[lane] : 0.0);
 }
 
 // exclusive prefix over threads of per-thread totals
 __device__ __forceinline__ double block_exclusive_scan(double v, double* sh) {
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
     double inc = v;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
@@ -304,11 +303,15 @@ __device__ __forceinline__ double block_exclusive_scan(double v, double* sh) {
     __syncthreads();
     if (lane == 31) sh[w] = inc;
     __syncthreads();
-    double base = 0.0;
-    for (int i = 0; i < w && i < nw; ++i) base += sh[i];
+    double tot = lane < nw ? sh[lane] : 0.0;   // warp totals, scanned by every warp
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const double n = __shfl_up_sync(0xffffffffu, tot, o);
+        if (lane >= o) tot += n;
+    }
+    const double base = w > 0 ? __shfl_sync(0xffffffffu, tot, w - 1) : 0.0;
     return base + inc - v;
 }
-
 #endif
 
 }  // namespace qg

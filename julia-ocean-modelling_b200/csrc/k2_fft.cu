@@ -215,6 +215,15 @@ __device__ __forceinline__ double load_gauge(const FftArgs& a, int member, doubl
     return block_sum(loc, sh);
 }
 
+// L2 prefetch of a row that a later loop iteration will read: `nthr` threads (index `t`) cover
+// `bytes` bytes, one request per 128-byte line.  Hides the HBM latency of the persistent loop's
+// next row behind the current row's passes (there are no spare registers to double-buffer in).
+__device__ __forceinline__ void prefetch_row_l2(const void* base, int bytes, int t, int nthr) {
+    const char* p = static_cast<const char*>(base);
+    for (int off = t * 128; off < bytes; off += nthr * 128)
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(p + off));
+}
+
 template <int LOG2N>
 struct FftLaunch {
     static constexpr int N = 1 << LOG2N;
@@ -412,6 +421,15 @@ k2_rfft_forward(const FftArgs a, int ngroups_per_member, int ngroups_total) {
         for (int t = 0; t < 8; ++t) {
             const double2 x1 = __ldg(q1 + lt + t * TPR), x2 = __ldg(q2 + lt + t * TPR);
             v[t] = make_double2(A0 * x1.x + A1 * x2.x, A0 * x1.y + A1 * x2.y);   // (q~[2n], q~[2n+1])
+        }
+        {   // next (row, field) of this CTA -> L2
+            const int gn = grp + gridDim.x;
+            if (gn < ngroups_total) {
+                const int mn = gn / ngroups_per_member;
+                const int rn = (gn - mn * ngroups_per_member) >> 1;
+                prefetch_row_l2(a.q1 + mn * a.mstride + a.g.at(0, rn), M * 8, lt, TPR);
+                prefetch_row_l2(a.q2 + mn * a.mstride + a.g.at(0, rn), M * 8, lt, TPR);
+            }
         }
         fft.template run<true>(v, s, lt);
         double2* __restrict__ out =

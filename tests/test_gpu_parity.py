@@ -249,3 +249,26 @@ def test_y_slab_decomposition_on_two_gpus():
                               os.path.join(root, "tests", "dist_slab_check.py"), str(M), str(P), "10"],
                              capture_output=True, text=True, timeout=600)
         assert "SLAB_CHECK_OK" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
+
+
+def test_initial_upload_and_graph_replay_match_plain_path(monkeypatch):
+    """qg_upload_initial_state (level 1 only, history and f_store zeroed on the device) followed by
+    a long qg_step (CUDA-graph replay of the 3-step cycle) gives bit-identical results to the
+    full upload and step-by-step launches."""
+    mo, mg = models(96, 64)
+    zeta, psi = o.initialise_model(mo, seed=9)
+    f = np.zeros_like(zeta)
+    za, pa, fa = zeta.copy(order="F"), psi.copy(order="F"), f.copy(order="F")
+    with qgb200.Session(mg) as s:
+        s.upload_initial(za, pa)
+        s.step(1, 23)                       # 2 Euler + 21 AB3 steps: 7 graph replays
+        s.download(za, pa, fa)
+    zb, pb, fb = zeta.copy(order="F"), psi.copy(order="F"), f.copy(order="F")
+    with qgb200.Session(mg) as s:
+        s.upload(zb, pb, fb)
+        for t in range(1, 24):              # one step per call: never enough steps left for a graph
+            s.step(t, 1)
+        s.download(zb, pb, fb)
+    assert np.array_equal(za, zb) and np.array_equal(pa, pb) and np.array_equal(fa, fb)
+    o.run_steps(mo, zeta, psi, f, o.make_factors(mo, "spectral"), 1, 23)
+    assert rel(pa, psi) < TOL_FIELD and rel(za, zeta) < TOL_FIELD

@@ -339,6 +339,13 @@ __global__ void __launch_bounds__(512) k3_ysolve(const YArgs a) {
 constexpr int TS_WC = 16;
 constexpr int TS_LD = 17;   // padded leading dimension of the per-chunk carry arrays
 
+#ifdef QG_K3_TRACE
+__device__ long long* g_k3_trace = nullptr;   // [CTA][8] clock64 stamps of thread 0
+#define K3_STAMP(i) do { if (tid == 0 && g_k3_trace) g_k3_trace[((size_t)blockIdx.y * gridDim.x + blockIdx.x) * 8 + (i)] = clock64(); } while (0)
+#else
+#define K3_STAMP(i) do { } while (0)
+#endif
+
 template <int MODE>   // 0: cyclic over the local rows; 1 / 2: y-slab mode, see YArgs::mode
 __global__ void __launch_bounds__(256, 3)
 k3_ysolve_tma(const __grid_constant__ CUtensorMap tmS, const YArgs a, int nchunk) {
@@ -366,6 +373,7 @@ k3_ysolve_tma(const __grid_constant__ CUtensorMap tmS, const YArgs a, int nchunk
     double* sY = sX + TS_WC;
     uint64_t* bar = reinterpret_cast<uint64_t*>(sY + TS_WC);
 
+    K3_STAMP(0);
     const int c0 = cr * nchunk;                 // first global chunk of this CTA
     const int nact = max(0, min(nchunk, C - c0));   // chunks that hold rows
     if (tid == 0) mbar_init(bar, 1);
@@ -390,7 +398,9 @@ k3_ysolve_tma(const __grid_constant__ CUtensorMap tmS, const YArgs a, int nchunk
     const bool mine = chunk < nchunk;   // the block is padded to whole warps
     const int len = (mine && c < C) ? min(32, P - j0) : 0;
     double* t = tile + (size_t)(mine ? chunk : 0) * 32 * TS_WC + l;
+    K3_STAMP(1);
     if (nact > 0) mbar_wait(bar, 0);
+    K3_STAMP(2);
 
     // ---- pass 1: zero-carry forward recurrence in place, forward end value and backward sum ----
     {
@@ -409,6 +419,7 @@ k3_ysolve_tma(const __grid_constant__ CUtensorMap tmS, const YArgs a, int nchunk
             sG[chunk * TS_LD + l] = G;
         }
     }
+    K3_STAMP(3);
     __syncthreads();
 
     // ---- carries (see k3_ysolve): one exchange round across the cluster ---------------------
@@ -453,7 +464,9 @@ k3_ysolve_tma(const __grid_constant__ CUtensorMap tmS, const YArgs a, int nchunk
         }
         if (slot == 0) { sFF[cl] = FFv; sRR[cl] = RRv; sX[cl] = Xv; sY[cl] = Yv; }
     }
+    K3_STAMP(4);
     cluster.sync();
+    K3_STAMP(5);
     for (int cb = warp; cb < TS_WC / 2; cb += nwarp) {
         const int cl = 2 * cb + csel;
         const int gc = (col0 + cl < ncol) ? col0 + cl : 0;
@@ -535,6 +548,7 @@ k3_ysolve_tma(const __grid_constant__ CUtensorMap tmS, const YArgs a, int nchunk
             sG[slot * TS_LD + cl] = fma(Rex, b_e, tex);
         }
     }
+    K3_STAMP(6);
     cluster.barrier_arrive();   // remote reads are done; matched by barrier_wait() before exit
     if (MODE == 1) {
         cluster.barrier_wait();
@@ -566,6 +580,7 @@ k3_ysolve_tma(const __grid_constant__ CUtensorMap tmS, const YArgs a, int nchunk
             if (l == 0) a.gpart[(int64_t)member * a.ngp + slab] = g;
         }
     }
+    K3_STAMP(7);
     cluster.barrier_wait();   // distributed shared memory must outlive every remote read
 }
 
@@ -634,8 +649,37 @@ static cudaError_t launch_tma_kernel(Handle* h, const YArgs& a) {
         if (e != cudaSuccess) return e;
         configured[a.mode] = cfg.dynamicSmemBytes;
     }
+#ifdef QG_K3_TRACE
+    static long long* dbuf = nullptr;
+    static int calls = 0;
+    const size_t nct = (size_t)cfg.gridDim.x * cfg.gridDim.y;
+    if (!dbuf) {
+        cudaMalloc((void**)&dbuf, nct * 8 * sizeof(long long));
+        cudaMemcpyToSymbol(g_k3_trace, &dbuf, sizeof(dbuf));
+    }
+    cudaError_t te;
+    {
+        KernelTimer t(h, QG_K_YSOLVE);
+        te = cudaLaunchKernelEx(&cfg, kern, h->tm_S, a, pl.ts_nchunk);
+    }
+    if (++calls == 20) {
+        cudaStreamSynchronize(h->stream);
+        std::vector<long long> hb(nct * 8);
+        cudaMemcpy(hb.data(), dbuf, hb.size() * sizeof(long long), cudaMemcpyDeviceToHost);
+        double sum[8] = {0};
+        for (size_t c = 0; c < nct; ++c)
+            for (int i = 1; i < 8; ++i) sum[i] += (double)(hb[c * 8 + i] - hb[c * 8 + i - 1]);
+        const char* nm[8] = {"", "setup+tma issue", "tma wait", "pass1", "stage1 scan", "cluster.sync", "stage2 closure", "sync+pass2"};
+        double tot = 0;
+        for (int i = 1; i < 8; ++i) tot += sum[i] / nct;
+        for (int i = 1; i < 8; ++i) fprintf(stderr, "K3TRACE %-16s %9.0f cycles\n", nm[i], sum[i] / nct);
+        fprintf(stderr, "K3TRACE %-16s %9.0f cycles (%zu CTAs)\n", "total", tot, nct);
+    }
+    return te;
+#else
     KernelTimer t(h, QG_K_YSOLVE);
     return cudaLaunchKernelEx(&cfg, kern, h->tm_S, a, pl.ts_nchunk);
+#endif
 }
 
 // y-slab mode: gather the k=0 column, solve it redundantly on every rank, sweep + exchange the

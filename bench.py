@@ -47,6 +47,18 @@ def model_args(M, P):
                 visc=100.0, r=1e-7, R_d=40.0 * KM, initial_kick=1e-6)
 
 
+def ncu_traffic(kernel, M, P):
+    """DRAM bytes per launch of `kernel` from the committed ncu --set full capture (profiles/), or None."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
+            t = json.load(f)
+        if list(t["grid"]) != [M, P]:
+            return None
+        return t["kernels"][kernel]["dram_bytes_per_launch"]
+    except Exception:
+        return None
+
+
 def peaks():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -339,7 +351,8 @@ def main():
                        "l2": "working set 2.7 GB per GPU >> 126 MB L2, no explicit flush",
                        "parallelism": f"member-per-gpu x{world}"},
             "roofline": {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s",
-                         "frac": ach / peak, "traffic": None, "peak_source": peak_src,
+                         "frac": ach / peak, "traffic": ncu_traffic(dom, M, P), "peak_source": peak_src,
+                         "algorithmic_bytes_per_launch": KERNEL_BYTES[dom] * cells,
                          "algorithmic_bytes_per_cell": KERNEL_BYTES[dom],
                          "step": {"achieved": STEP_BYTES * cells * K / (ms_total * 1e-3) / 1e9,
                                   "frac": STEP_BYTES * cells * K / (ms_total * 1e-3) / 1e9 / peak,

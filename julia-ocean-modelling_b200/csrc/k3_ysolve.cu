@@ -25,6 +25,8 @@
 // total from the real part of every Poisson coefficient of row 0.  k3_gauge evaluates
 // psi~1(0,0), which k4 subtracts (the pinned unknown is exactly zero in the reference).
 #include <cooperative_groups.h>
+#include <cstdio>
+#include <cstdlib>
 
 #include "qg_internal.cuh"
 
@@ -584,6 +586,303 @@ k3_ysolve_tma(const __grid_constant__ CUtensorMap tmS, const YArgs a, int nchunk
     cluster.barrier_wait();   // distributed shared memory must outlive every remote read
 }
 
+// ---- persistent, software-pipelined variant (single-GPU mode) ----------------------------------
+// Same slab / cluster geometry and carry algebra as k3_ysolve_tma, rebuilt around what the phase
+// trace of that kernel showed (QG_K3_TRACE): a dependent FP64 operation costs ~40 cycles here,
+// one thread issuing 16 TMA boxes costs ~4 k cycles, cluster.sync() waits for the CTA's global
+// stores to drain, and a tile holds its shared memory for the whole CTA lifetime although it is
+// in flight for a quarter of it.
+//   * A cluster stays on its SMs and walks over the column slabs.  As soon as a CTA's tile has
+//     landed it is moved into registers (32 rows per thread) and the TMA copies of the NEXT slab
+//     (two 256-row boxes + the slab's column table) are issued into the same buffer: the load of
+//     slab n+1 overlaps the sweeps, the exchange and the stores of slab n.
+//   * The 32-row recurrences run as four interleaved 8-row segments with a three-step carry fix
+//     (12 dependent steps instead of 32); forward then backward, both with zero carries, leave
+//     z_loc in registers, F = y_loc(last row), G = z_loc(first row).
+//   * Once the carries (A from below, B from above) are known the solution is element-wise,
+//         u[i] = kap * ( z_loc[i] + A * cA[i] + B * cB[i] ),
+//         cA[i] = r^(i+1) * sum_{m<32-i} r^(2m),   cB[i] = r^(32-i),
+//     with cA, cB and every other per-column constant in one table (Plan::coltab) that arrives
+//     by TMA with the tile; the stores go straight from registers (a half-warp = one 128-byte line).
+//   * The cluster exchange is push-based: every CTA writes its aggregate (FF, RR, X, Y)[16] into
+//     the shared memory of all peers with st.async, completing on the peer's mbarrier.  No cluster
+//     barrier in the loop, hence no wait for outstanding global stores.
+//   * CTA-level closure by shuffles (lane i mod 8 = CTA i), like the chunk level.
+constexpr int TP_THREADS = 256;
+constexpr int CT_ROWS = 72;   // rows of Plan::coltab, see build_plan()
+constexpr int CT_CA = 0, CT_CB = 32, CT_R = 64, CT_KAP = 65, CT_RHO = 66, CT_H = 67, CT_INV1 = 68, CT_PINW = 69,
+              CT_GW = 70;
+
+__device__ __forceinline__ uint32_t map_to_cta(uint32_t saddr, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(saddr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void st_async_2(uint32_t raddr, double x, double y, uint32_t rbar) {
+    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v2.b64 [%0], {%1, %2}, [%3];" ::"r"(raddr),
+                 "l"(__double_as_longlong(x)), "l"(__double_as_longlong(y)), "r"(rbar)
+                 : "memory");
+}
+
+#ifdef QG_K3_TRACE
+#define K3_ACC(i) do { if (tid == 0) { const long long now_ = clock64(); acc[i] += now_ - last; last = now_; } } while (0)
+#else
+#define K3_ACC(i) do { } while (0)
+#endif
+
+__global__ void __launch_bounds__(TP_THREADS, 2)
+k3_ysolve_pipe(const __grid_constant__ CUtensorMap tmS, const __grid_constant__ CUtensorMap tmT, const YArgs a,
+               int nchunk, int boxrows, int nslab, int nwork) {
+    extern __shared__ __align__(128) unsigned char ts_raw[];
+    cg::cluster_group cluster = cg::this_cluster();
+    const int CS = (int)cluster.num_blocks();
+    const int cr = (int)cluster.block_rank();
+    const int ncluster = gridDim.x / CS;
+    const int cid = blockIdx.x / CS;
+    const int C = a.pl.C, P = a.pl.P, ncol = a.pl.ncol;
+    const int tid = threadIdx.x;
+    const int chunk = tid >> 4, l = tid & 15;
+    const int warp = tid >> 5, lane = tid & 31;
+    const int slot = lane & 15, csel = lane >> 4;
+    const int cl = 2 * warp + csel;                 // exchange phases: this lane's column within the slab
+
+    double* tile = reinterpret_cast<double*>(ts_raw);                  // [nchunk*32][16]
+    double* ctab = tile + (size_t)nchunk * 32 * TS_WC;                 // [2 parities][CT_ROWS][16]
+    double* sF = ctab + 2 * CT_ROWS * TS_WC;                           // [nchunk][TS_LD]
+    double* sG = sF + nchunk * TS_LD;
+    double* sEx = sG + nchunk * TS_LD;                                 // [2 parities][8 CTAs][16 cols][FF,RR,X,Y]
+    uint64_t* bar = reinterpret_cast<uint64_t*>(sEx + 2 * 8 * TS_WC * 4);   // [0] tile, [1..2] exchange parity
+
+    const int c0 = cr * nchunk;                     // first global chunk of this CTA
+    const int nact = max(0, min(nchunk, C - c0));   // chunks that hold rows (all of them full: P % 32 == 0)
+    const bool live = chunk < nact;                 // this thread owns a chunk with rows
+    const int j0 = (c0 + chunk) * 32;
+    const double* t = tile + (size_t)(live ? chunk : 0) * 32 * TS_WC + l;
+    const bool act = slot < nact;                   // scan lanes that stand for a chunk with rows
+    const int nbox = (nchunk * 32) / boxrows;
+    const uint32_t tx_bytes = (uint32_t)((nact > 0 ? nchunk * 32 : 0) + CT_ROWS) * TS_WC * sizeof(double);
+
+    auto issue = [&](int w, int par) {   // one thread: tile boxes + column table of work item w
+        const int member = w / nslab, slab = w - member * nslab;
+        mbar_expect_tx(&bar[0], tx_bytes);
+        if (nact > 0)
+            for (int k = 0; k < nbox; ++k)
+                tma_load_2d(tile + (size_t)k * boxrows * TS_WC, &tmS, slab * TS_WC, member * P + c0 * 32 + k * boxrows,
+                            &bar[0]);
+        tma_load_2d(ctab + (size_t)par * CT_ROWS * TS_WC, &tmT, slab * TS_WC, 0, &bar[0]);
+    };
+    if (tid == 0) {
+        mbar_init(&bar[0], 1);
+        mbar_init(&bar[1], 1);
+        mbar_init(&bar[2], 1);
+        if (cid < nwork) issue(cid, 0);
+    }
+    cluster.sync();   // every CTA's mbarriers exist before anyone pushes to them
+
+#ifdef QG_K3_TRACE
+    long long acc[8] = {0, 0, 0, 0, 0, 0, 0, 0}, last = clock64();
+#endif
+    uint32_t it = 0;
+    for (int w = cid; w < nwork; w += ncluster, ++it) {
+        const int member = w / nslab, slab = w - member * nslab;
+        const int col0 = slab * TS_WC;
+        const int col = col0 + l;
+        const int par = it & 1;
+        const double* ct = ctab + (size_t)par * CT_ROWS * TS_WC;
+        double* ex = sEx + (size_t)par * 8 * TS_WC * 4;
+        uint64_t* xbar = &bar[1 + par];
+        const double pinscale = a.pinned ? a.scal[member * 4 + 0] : 0.0;
+        if (tid == 0) mbar_expect_tx(xbar, (uint32_t)CS * TS_WC * 4 * sizeof(double));
+        K3_ACC(0);
+        mbar_wait(&bar[0], par);
+        K3_ACC(1);
+        double v[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = live ? t[i * TS_WC] : 0.0;
+        __syncthreads();   // the tile is in registers: the buffer is free for the next slab
+        if (tid == 0 && w + ncluster < nwork) issue(w + ncluster, par ^ 1);
+        K3_ACC(2);
+
+        const double r = ct[CT_R * TS_WC + l];
+        {
+            // the reference's pinned node: the right-hand side of row 0 loses the column total
+            if (live && a.row0 + j0 == 0) v[0] -= ct[CT_PINW * TS_WC + l] * pinscale;
+            double p8[8];   // r^(k+1) = cB[31-k]
+#pragma unroll
+            for (int k = 0; k < 8; ++k) p8[k] = ct[(CT_CB + 31 - k) * TS_WC + l];
+            const double r8 = p8[7];
+            // forward, zero carry: four interleaved 8-row chains, then the segment carries
+#pragma unroll
+            for (int k = 1; k < 8; ++k)
+#pragma unroll
+                for (int sg = 0; sg < 4; ++sg) v[8 * sg + k] = fma(r, v[8 * sg + k - 1], v[8 * sg + k]);
+            const double f1 = v[7], f2 = fma(r8, f1, v[15]), f3 = fma(r8, f2, v[23]);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                v[8 + k] = fma(p8[k], f1, v[8 + k]);
+                v[16 + k] = fma(p8[k], f2, v[16 + k]);
+                v[24 + k] = fma(p8[k], f3, v[24 + k]);
+            }
+            const double F = v[31];
+            // backward, zero carry
+#pragma unroll
+            for (int k = 6; k >= 0; --k)
+#pragma unroll
+                for (int sg = 0; sg < 4; ++sg) v[8 * sg + k] = fma(r, v[8 * sg + k + 1], v[8 * sg + k]);
+            const double e3 = v[24], e2 = fma(r8, e3, v[16]), e1 = fma(r8, e2, v[8]);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                v[k] = fma(p8[7 - k], e1, v[k]);
+                v[8 + k] = fma(p8[7 - k], e2, v[8 + k]);
+                v[16 + k] = fma(p8[7 - k], e3, v[16 + k]);
+            }
+            if (chunk < nchunk) {
+                sF[chunk * TS_LD + l] = F;
+                sG[chunk * TS_LD + l] = v[0];
+            }
+        }
+        __syncthreads();
+        K3_ACC(3);
+
+        // ---- carries: warp-level cyclic reduction per column pair, one push-based exchange ----------
+        {
+            const double rho = act ? ct[CT_RHO * TS_WC + cl] : 1.0;
+            const double hh = act ? ct[CT_H * TS_WC + cl] : 0.0;
+            const double inv1 = ct[CT_INV1 * TS_WC + cl];
+            const double F = act ? sF[slot * TS_LD + cl] : 0.0;
+            const double G = act ? sG[slot * TS_LD + cl] : 0.0;
+            double R = rho, tt = F;
+#pragma unroll
+            for (int d = 1; d < 16; d <<= 1) {
+                const double Rp = __shfl_up_sync(0xffffffffu, R, d, 16);
+                const double tp = __shfl_up_sync(0xffffffffu, tt, d, 16);
+                if (slot >= d) {
+                    tt = fma(R, tp, tt);
+                    R *= Rp;
+                }
+            }
+            const double FFv = __shfl_sync(0xffffffffu, tt, 15, 16);
+            const double RRv = __shfl_sync(0xffffffffu, R, 15, 16);
+            double Rpre = __shfl_up_sync(0xffffffffu, R, 1, 16);
+            double pF = __shfl_up_sync(0xffffffffu, tt, 1, 16);
+            if (slot == 0) { Rpre = 1.0; pF = 0.0; }
+            double Xv = Rpre * fma(hh, pF, G), Yv = Rpre * (hh * Rpre);
+#pragma unroll
+            for (int d = 8; d > 0; d >>= 1) {
+                Xv += __shfl_xor_sync(0xffffffffu, Xv, d, 16);
+                Yv += __shfl_xor_sync(0xffffffffu, Yv, d, 16);
+            }
+            if (slot < CS) {   // lane `slot` pushes this column's aggregate to CTA `slot`
+                const uint32_t dst = map_to_cta(smem_u32(ex + ((size_t)cr * TS_WC + cl) * 4), (uint32_t)slot);
+                const uint32_t rb = map_to_cta(smem_u32(xbar), (uint32_t)slot);
+                st_async_2(dst, FFv, RRv, rb);
+                st_async_2(dst + 16, Xv, Yv, rb);
+            }
+            K3_ACC(4);
+            mbar_wait(xbar, (it >> 1) & 1);
+            K3_ACC(5);
+            // CTA-level closure, again as a parallel cyclic reduction: lane i (mod 8) of the half-warp
+            // holds CTA i's aggregate and the affine maps compose by shuffles
+            const int i8 = slot & 7;
+            double FFl = 0.0, RRl = 1.0, Xl = 0.0, Yl = 0.0;
+            if (i8 < CS) {
+                const double2 q0 = *reinterpret_cast<const double2*>(ex + ((size_t)i8 * TS_WC + cl) * 4);
+                const double2 q1 = *reinterpret_cast<const double2*>(ex + ((size_t)i8 * TS_WC + cl) * 4 + 2);
+                FFl = q0.x; RRl = q0.y; Xl = q1.x; Yl = q1.y;
+            }
+            double R1 = RRl, T1 = FFl;   // inclusive forward composition over CTAs 0..i
+#pragma unroll
+            for (int d = 1; d < 8; d <<= 1) {
+                const double Rp = __shfl_up_sync(0xffffffffu, R1, d, 8);
+                const double Tp = __shfl_up_sync(0xffffffffu, T1, d, 8);
+                if (i8 >= d) {
+                    T1 = fma(R1, Tp, T1);
+                    R1 *= Rp;
+                }
+            }
+            // carry into CTA 0: cyclic closure (y at the last row)
+            const double as0 = __shfl_sync(0xffffffffu, T1, 7, 8) * inv1;
+            double Rx = __shfl_up_sync(0xffffffffu, R1, 1, 8), Tx = __shfl_up_sync(0xffffffffu, T1, 1, 8);
+            if (i8 == 0) { Rx = 1.0; Tx = 0.0; }
+            const double as_i = fma(Rx, as0, Tx);          // forward carry into CTA i
+            const double GGp = fma(Yl, as_i, Xl);          // CTA i's backward aggregate with its true carry
+            double R2 = RRl, T2 = GGp;   // inclusive backward composition over CTAs 7..i
+#pragma unroll
+            for (int d = 1; d < 8; d <<= 1) {
+                const double Rp = __shfl_down_sync(0xffffffffu, R2, d, 8);
+                const double Tp = __shfl_down_sync(0xffffffffu, T2, d, 8);
+                if (i8 + d < 8) {
+                    T2 = fma(R2, Tp, T2);
+                    R2 *= Rp;
+                }
+            }
+            // carry into the last CTA: cyclic closure (z at row 0)
+            const double blast = __shfl_sync(0xffffffffu, T2, 0, 8) * inv1;
+            Rx = __shfl_down_sync(0xffffffffu, R2, 1, 8);
+            Tx = __shfl_down_sync(0xffffffffu, T2, 1, 8);
+            if (i8 == 7) { Rx = 1.0; Tx = 0.0; }
+            const double be_i = fma(Rx, blast, Tx);        // backward carry into CTA i
+            const double a_s = __shfl_sync(0xffffffffu, as_i, cr, 8);
+            const double b_e = __shfl_sync(0xffffffffu, be_i, cr, 8);
+            const double A = fma(Rpre, a_s, pF);
+            const double Gp = fma(A, hh, G);
+            // inclusive backward (suffix) scan of x -> rho x + G'
+            double ts = Gp;
+            R = rho;
+#pragma unroll
+            for (int d = 1; d < 16; d <<= 1) {
+                const double Rp = __shfl_down_sync(0xffffffffu, R, d, 16);
+                const double tp = __shfl_down_sync(0xffffffffu, ts, d, 16);
+                if (slot + d < 16) {
+                    ts = fma(R, tp, ts);
+                    R *= Rp;
+                }
+            }
+            double Rex = __shfl_down_sync(0xffffffffu, R, 1, 16), tex = __shfl_down_sync(0xffffffffu, ts, 1, 16);
+            if (slot == 15) { Rex = 1.0; tex = 0.0; }
+            if (slot < nchunk) {
+                sF[slot * TS_LD + cl] = A;                       // A overwrites F, B overwrites G
+                sG[slot * TS_LD + cl] = fma(Rex, b_e, tex);
+            }
+        }
+        __syncthreads();
+        K3_ACC(6);
+
+        // ---- apply: element-wise from registers, a half-warp stores one 128-byte row segment ---------
+        if (live) {
+            const double A = sF[chunk * TS_LD + l], B = sG[chunk * TS_LD + l];
+            const double kap = ct[CT_KAP * TS_WC + l];
+            const bool cvalid = col < ncol;
+            const double* __restrict__ k0 = a.k0sol + (int64_t)member * a.preP + a.row0 + j0;
+            double* out = a.S + member * a.sstride + (int64_t)j0 * ncol + (cvalid ? col : 0);
+            double u0 = 0.0;
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+                double u = kap * fma(A, ct[(CT_CA + i) * TS_WC + l], fma(B, ct[(CT_CB + i) * TS_WC + l], v[i]));
+                if (col == 0) u = k0[i];
+                if (cvalid) *out = u;
+                out += ncol;
+                if (i == 0) u0 = u;
+            }
+            // psi~1 at node (0,0) = sum over the x wavenumbers of row 0 of the solved Poisson field:
+            // the half-warp that owns global row 0 leaves this slab's share for K4 to add up
+            if (a.gpart != nullptr && a.row0 + j0 == 0) {   // uniform over the half-warp
+                double g = ct[CT_GW * TS_WC + l] * u0;
+#pragma unroll
+                for (int d = 8; d > 0; d >>= 1) g += __shfl_xor_sync(0xffffu << (tid & 16), g, d, 16);
+                if (l == 0) a.gpart[(int64_t)member * a.ngp + slab] = g;
+            }
+        }
+        K3_ACC(7);
+        // sF / sG and the other table parity are rewritten only after the next iteration's barriers
+    }
+#ifdef QG_K3_TRACE
+    if (tid == 0 && g_k3_trace)
+        for (int i = 0; i < 8; ++i) g_k3_trace[(size_t)blockIdx.x * 8 + i] = acc[i];
+#endif
+    cluster.sync();   // no CTA leaves while a peer may still push to it or read its aggregates
+}
+
 // y-slab mode: cyclic closure over the ranks.  aggr_all[g][4][ncol] holds every rank's
 // (FF, RR, X, Y); thread per column computes the forward carry entering this rank from below
 // (Ain) and the backward carry entering it from above (Bin).  Same algebra as the CTA level.
@@ -625,14 +924,18 @@ k3_rank_closure(const double* __restrict__ aggr_all, int nranks, int rank, int n
     Bin[col] = b_e;
 }
 
+static int env_int(const char* name, int dflt) {
+    const char* v = getenv(name);
+    return v ? atoi(v) : dflt;
+}
+
 static cudaError_t launch_tma_kernel(Handle* h, const YArgs& a) {
     const Plan& pl = h->plan;
+    static const int use_v1 = env_int("QG_K3_V1", 0);
+    static const int ncl_env = env_int("QG_K3_NCL", 0);
     const int nslab = (pl.ncol + TS_WC - 1) / TS_WC;
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(nslab * pl.ts_CS, h->nm, 1);
-    cfg.blockDim = dim3(((16 * pl.ts_nchunk + 31) / 32) * 32, 1, 1);
-    cfg.dynamicSmemBytes = ((size_t)pl.ts_nchunk * 32 * TS_WC + 32 * TS_WC + 2 * pl.ts_nchunk * TS_LD +
-                            4 * TS_WC) * sizeof(double) + 16;
     cfg.stream = h->stream;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
@@ -641,18 +944,47 @@ static cudaError_t launch_tma_kernel(Handle* h, const YArgs& a) {
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    static size_t configured[3] = {0, 0, 0};
-    auto kern = a.mode == 1 ? k3_ysolve_tma<1> : (a.mode == 2 ? k3_ysolve_tma<2> : k3_ysolve_tma<0>);
-    if (cfg.dynamicSmemBytes > configured[a.mode]) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    if (use_v1 || a.mode != 0 || !pl.tp_ok) {
+        cfg.blockDim = dim3(((16 * pl.ts_nchunk + 31) / 32) * 32, 1, 1);
+        cfg.dynamicSmemBytes = ((size_t)pl.ts_nchunk * 32 * TS_WC + 32 * TS_WC + 2 * pl.ts_nchunk * TS_LD +
+                                4 * TS_WC) * sizeof(double) + 16;
+        static size_t configured[3] = {0, 0, 0};
+        auto kern = a.mode == 1 ? k3_ysolve_tma<1> : (a.mode == 2 ? k3_ysolve_tma<2> : k3_ysolve_tma<0>);
+        if (cfg.dynamicSmemBytes > configured[a.mode]) {
+            cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                 (int)cfg.dynamicSmemBytes);
+            if (e != cudaSuccess) return e;
+            configured[a.mode] = cfg.dynamicSmemBytes;
+        }
+        KernelTimer t(h, QG_K_YSOLVE);
+        return cudaLaunchKernelEx(&cfg, kern, h->tm_S, a, pl.ts_nchunk);
+    }
+    // single-GPU mode: persistent clusters, one wave
+    static size_t configured_p = 0;
+    cfg.blockDim = dim3(TP_THREADS, 1, 1);
+    cfg.dynamicSmemBytes = ((size_t)pl.ts_nchunk * 32 * TS_WC + 2 * CT_ROWS * TS_WC + 2 * pl.ts_nchunk * TS_LD +
+                            2 * 8 * TS_WC * 4) * sizeof(double) + 32;
+    if (cfg.dynamicSmemBytes > configured_p) {
+        cudaError_t e = cudaFuncSetAttribute(k3_ysolve_pipe, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              (int)cfg.dynamicSmemBytes);
         if (e != cudaSuccess) return e;
-        configured[a.mode] = cfg.dynamicSmemBytes;
+        configured_p = cfg.dynamicSmemBytes;
     }
+    if (h->plan.tp_ncl == 0) {   // clusters the device holds at once
+        int ncl = 0;
+        cfg.gridDim = dim3(nslab * pl.ts_CS * h->nm, 1, 1);
+        if (cudaOccupancyMaxActiveClusters(&ncl, k3_ysolve_pipe, &cfg) == cudaSuccess && ncl > 0) h->plan.tp_ncl = ncl;
+        else { h->plan.tp_ncl = 2 * 148 / pl.ts_CS; (void)cudaGetLastError(); }
+        if (ncl_env > 0) h->plan.tp_ncl = ncl_env;
+        if (getenv("QG_VERBOSE")) fprintf(stderr, "qgb200: y-solve persistent clusters: %d x %d CTAs\n", h->plan.tp_ncl, pl.ts_CS);
+    }
+    const int nwork = nslab * h->nm;
+    const int ncl = h->plan.tp_ncl < nwork ? h->plan.tp_ncl : nwork;
+    cfg.gridDim = dim3(ncl * pl.ts_CS, 1, 1);
 #ifdef QG_K3_TRACE
     static long long* dbuf = nullptr;
     static int calls = 0;
-    const size_t nct = (size_t)cfg.gridDim.x * cfg.gridDim.y;
+    const size_t nct = (size_t)cfg.gridDim.x;
     if (!dbuf) {
         cudaMalloc((void**)&dbuf, nct * 8 * sizeof(long long));
         cudaMemcpyToSymbol(g_k3_trace, &dbuf, sizeof(dbuf));
@@ -660,7 +992,7 @@ static cudaError_t launch_tma_kernel(Handle* h, const YArgs& a) {
     cudaError_t te;
     {
         KernelTimer t(h, QG_K_YSOLVE);
-        te = cudaLaunchKernelEx(&cfg, kern, h->tm_S, a, pl.ts_nchunk);
+        te = cudaLaunchKernelEx(&cfg, k3_ysolve_pipe, h->tm_S2, h->tm_T, a, pl.ts_nchunk, pl.tp_boxrows, nslab, nwork);
     }
     if (++calls == 20) {
         cudaStreamSynchronize(h->stream);
@@ -668,17 +1000,19 @@ static cudaError_t launch_tma_kernel(Handle* h, const YArgs& a) {
         cudaMemcpy(hb.data(), dbuf, hb.size() * sizeof(long long), cudaMemcpyDeviceToHost);
         double sum[8] = {0};
         for (size_t c = 0; c < nct; ++c)
-            for (int i = 1; i < 8; ++i) sum[i] += (double)(hb[c * 8 + i] - hb[c * 8 + i - 1]);
-        const char* nm[8] = {"", "setup+tma issue", "tma wait", "pass1", "stage1 scan", "cluster.sync", "stage2 closure", "sync+pass2"};
+            for (int i = 0; i < 8; ++i) sum[i] += (double)hb[c * 8 + i];
+        const char* nm[8] = {"loop top", "tma wait", "tile->regs+sync+issue", "sweeps+sync", "publish scan+push", "exchange wait",
+                             "closure+sync", "apply+stores"};
+        const double iters = (double)nwork / ncl;
         double tot = 0;
-        for (int i = 1; i < 8; ++i) tot += sum[i] / nct;
-        for (int i = 1; i < 8; ++i) fprintf(stderr, "K3TRACE %-16s %9.0f cycles\n", nm[i], sum[i] / nct);
-        fprintf(stderr, "K3TRACE %-16s %9.0f cycles (%zu CTAs)\n", "total", tot, nct);
+        for (int i = 0; i < 8; ++i) tot += sum[i] / nct / iters;
+        for (int i = 0; i < 8; ++i) fprintf(stderr, "K3TRACE %-22s %9.0f cycles/iter\n", nm[i], sum[i] / nct / iters);
+        fprintf(stderr, "K3TRACE %-22s %9.0f cycles/iter (%zu CTAs, %.1f iters)\n", "total", tot, nct, iters);
     }
     return te;
 #else
     KernelTimer t(h, QG_K_YSOLVE);
-    return cudaLaunchKernelEx(&cfg, kern, h->tm_S, a, pl.ts_nchunk);
+    return cudaLaunchKernelEx(&cfg, k3_ysolve_pipe, h->tm_S2, h->tm_T, a, pl.ts_nchunk, pl.tp_boxrows, nslab, nwork);
 #endif
 }
 

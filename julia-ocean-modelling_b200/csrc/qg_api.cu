@@ -191,6 +191,7 @@ cudaError_t build_plan(Handle* h) {
     const long double dx2 = (long double)h->prm.dx * (long double)h->prm.dx;
     std::vector<double> rtab(pl.ncol), kap(pl.ncol), rho32(pl.ncol), h32(pl.ncol), rhoL(pl.ncol),
         hL(pl.ncol), inv1(pl.ncol), pinw(pl.ncol), gw(pl.ncol);
+    std::vector<long double> rlong(pl.ncol);
     for (int col = 0; col < pl.ncol; ++col) {
         const int s = col >> 1, part = col & 1;
         int field, k;
@@ -208,6 +209,7 @@ cudaError_t build_plan(Handle* h) {
         const long double geo32 = singular ? 0.0L : r * (1.0L - r32 * r32) / (1.0L - r * r);
         const long double geoL = singular ? 0.0L : r * (1.0L - rL * rL) / (1.0L - r * r);
         rtab[col] = (double)r;
+        rlong[col] = r;
         kap[col] = singular ? 0.0 : (double)(-r * dx2 / M);
         rho32[col] = (double)r32;
         rhoL[col] = (double)rL;
@@ -231,6 +233,37 @@ cudaError_t build_plan(Handle* h) {
     if ((e = upload_vec(&pl.pinw, pinw)) != cudaSuccess) return e;
     if ((e = upload_vec(&pl.gw, gw)) != cudaSuccess) return e;
     pl.ngp = (pl.ncol + 15) / 16;
+    // persistent y-solve (k3_ysolve_pipe): needs whole 32-row chunks; one TMA box of <= 256 rows
+    // (or two equal ones) per CTA tile, and all per-column constants in one table so that they
+    // arrive with the tile:  rows 0-31 cA[i] = r^(i+1) * sum_{m<32-i} r^(2m), rows 32-63
+    // cB[i] = r^(32-i), then r, kap, r^32, h32, 1/(1-r^P), pin weight, gauge weight, spare.
+    pl.tp_ok = (pl.ts_ok && P % 32 == 0 && h->dist_n == 1) ? 1 : 0;
+    pl.tp_boxrows = pl.ts_nchunk * 32 <= 256 ? pl.ts_nchunk * 32 : pl.ts_nchunk * 16;
+    if (pl.tp_ok) {
+        const int NR = 72;
+        std::vector<double> ct((size_t)NR * pl.ncol, 0.0);
+        for (int col = 0; col < pl.ncol; ++col) {
+            const long double r = (long double)rtab[col] == 0.0L ? 0.0L : rlong[col];
+            long double rp[34];
+            rp[0] = 1.0L;
+            for (int i = 1; i < 34; ++i) rp[i] = rp[i - 1] * r;
+            long double gs[34];   // gs[n] = sum_{m<n} r^(2m)
+            gs[0] = 0.0L;
+            for (int n = 1; n < 34; ++n) gs[n] = gs[n - 1] + rp[n - 1] * rp[n - 1];
+            for (int i = 0; i < 32; ++i) {
+                ct[(size_t)i * pl.ncol + col] = (double)(rp[i + 1] * gs[32 - i]);
+                ct[(size_t)(32 + i) * pl.ncol + col] = (double)rp[32 - i];
+            }
+            ct[(size_t)64 * pl.ncol + col] = rtab[col];
+            ct[(size_t)65 * pl.ncol + col] = kap[col];
+            ct[(size_t)66 * pl.ncol + col] = rho32[col];
+            ct[(size_t)67 * pl.ncol + col] = h32[col];
+            ct[(size_t)68 * pl.ncol + col] = inv1[col];
+            ct[(size_t)69 * pl.ncol + col] = pinw[col];
+            ct[(size_t)70 * pl.ncol + col] = gw[col];
+        }
+        if ((e = upload_vec(&pl.coltab, ct)) != cudaSuccess) return e;
+    }
     h->plan_ok = true;
     return cudaSuccess;
 }
@@ -239,6 +272,7 @@ void free_plan(Handle* h) {
     Plan& pl = h->plan;
     cudaFree(pl.tw); cudaFree(pl.rtab); cudaFree(pl.kap); cudaFree(pl.rho32); cudaFree(pl.h32);
     cudaFree(pl.rhoL); cudaFree(pl.hL); cudaFree(pl.inv1mrP); cudaFree(pl.pinw); cudaFree(pl.gw);
+    cudaFree(pl.coltab);
     memset(&pl, 0, sizeof(pl));
     h->plan_ok = false;
 }
@@ -287,6 +321,24 @@ static int make_tensor_map_S(Handle* h) {
         char b[128];
         snprintf(b, sizeof(b), "cuTensorMapEncodeTiled (spectral) failed with CUresult %d", (int)r);
         return fail(h, QG_ERR_CUDA, b);
+    }
+    if (h->plan.tp_ok) {   // persistent y-solve: big tile boxes and the column table
+        const cuuint32_t box2[2] = {16, (cuuint32_t)h->plan.tp_boxrows};
+        r = encode(&h->tm_S2, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, h->S, dims, strides, box2, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r == CUDA_SUCCESS) {
+            const cuuint64_t dimsT[2] = {(cuuint64_t)h->plan.ncol, 72};
+            const cuuint32_t boxT[2] = {16, 72};
+            r = encode(&h->tm_T, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, h->plan.coltab, dimsT, strides, boxT, estr,
+                       CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                       CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        }
+        if (r != CUDA_SUCCESS) {
+            char b[128];
+            snprintf(b, sizeof(b), "cuTensorMapEncodeTiled (persistent y-solve) failed with CUresult %d", (int)r);
+            return fail(h, QG_ERR_CUDA, b);
+        }
     }
     return QG_OK;
 }

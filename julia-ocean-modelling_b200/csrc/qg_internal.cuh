@@ -68,6 +68,9 @@ struct Plan {
     int lenLast;             // rows in the last chunk
     int wpc, CS, m;          // warps per CTA, cluster size, chunks per warp (register variant)
     int ts_ok, ts_CS, ts_nchunk;   // TMA-staged variant: usable, cluster size, chunks per CTA
+    int tp_ncl;              // persistent variant: clusters resident at once (0 = not queried yet)
+    int tp_ok, tp_boxrows;   // persistent variant usable (P % 32 == 0); rows per TMA box (<= 256)
+    double* coltab;          // [72][ncol] per-column constants of the persistent y-solve (k3_ysolve.cu)
     double2* tw;             // exp(-2 pi i n / M), n < M
     double *rtab, *kap, *rho32, *h32, *rhoL, *hL, *inv1mrP, *pinw, *gw;   // per real column
     int ngp;                 // gauge partial sums per member (= slabs of the TMA y-solve)
@@ -152,6 +155,7 @@ struct Handle {
     int pcur = 0;                    // slot of the newest level of psi
     bool have_state = false;
     CUtensorMap tm_q, tm_psi, tm_S;
+    CUtensorMap tm_S2, tm_T;         // persistent y-solve: big tile boxes, column table
     int k1_ty = 16;                  // K1 tile height (8, 12, 16 or 24; env QG_K1_TY)
     Plan plan;
     bool plan_ok = false;

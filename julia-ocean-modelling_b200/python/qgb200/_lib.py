@@ -10,7 +10,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.normpath(os.path.join(_HERE, "..", "..", "lib", "libqgb200.so"))
+# QGB200_LIB points at another build of the same library (e.g. one compiled with -DQG_K3_TRACE)
+LIB_PATH = os.environ.get("QGB200_LIB") or os.path.normpath(os.path.join(_HERE, "..", "..", "lib", "libqgb200.so"))
 
 QG_NKERNELS = 8
 

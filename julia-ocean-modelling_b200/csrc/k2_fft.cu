@@ -24,6 +24,8 @@
 // The base twiddles come from a table evaluated in extended precision on the host.
 // Non-power-of-two M (the reference benchmarks M = 8:8:128) takes a direct O(M^2) DFT
 // path with the same spectral layout.
+#include <cstdlib>
+
 #include "qg_internal.cuh"
 
 namespace qg {
@@ -371,6 +373,250 @@ k4_fft_inverse(const FftArgs a, int ngroups_per_member, int ngroups_total) {
 }
 
 // ---------------------------------------------------------------------------------------
+// Radix-16 variant for N = 16^n (M = 4096, the headline grid, and M = 256): 16 points per
+// thread, N/16 threads per row.  Both transforms are bound by shared-memory wavefronts (ncu:
+// LSU data pipe 66 %, DRAM 44 %), and radix-16 needs one exchange less per row (3 passes
+// instead of 4 at N = 4096).  Same Stockham indexing, same spectral layout.
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ int swz16(int i) { return i ^ ((i >> 4) & 7); }
+
+// 16-point DFT in place, natural order output: X[u] = sum_t a[t] exp(SIGN * 2 pi i t u / 16)
+template <int SIGN>
+__device__ __forceinline__ void bfly16(double2 (&a)[16]) {
+    const double c1 = 0.92387953251128675613, s1 = 0.38268343236508977173, h = 0.70710678118654752440;
+    // step 1: 4-point DFTs over t = c + 4m  ->  y[c][q] stored at a[c + 4q]
+#pragma unroll
+    for (int c = 0; c < 4; ++c) bfly4<SIGN>(a[c], a[c + 4], a[c + 8], a[c + 12]);
+    // step 2: twiddles W16^(c q), W16 = exp(SIGN * 2 pi i / 16)
+    {
+        const double2 W1 = make_double2(c1, SIGN * s1), W2 = make_double2(h, SIGN * h), W3 = make_double2(s1, SIGN * c1);
+        a[1 + 4] = cmul(a[1 + 4], W1);                                  // c=1,q=1
+        a[1 + 8] = cmul(a[1 + 8], W2);                                  // c=1,q=2
+        a[1 + 12] = cmul(a[1 + 12], W3);                                // c=1,q=3
+        a[2 + 4] = cmul(a[2 + 4], W2);                                  // c=2,q=1
+        a[2 + 8] = muli<SIGN>(a[2 + 8]);                                // c=2,q=2: W16^4 = SIGN i
+        a[2 + 12] = cmul(a[2 + 12], make_double2(-h, SIGN * h));        // c=2,q=3: W16^6
+        a[3 + 4] = cmul(a[3 + 4], W3);                                  // c=3,q=1
+        a[3 + 8] = cmul(a[3 + 8], make_double2(-h, SIGN * h));          // c=3,q=2: W16^6
+        a[3 + 12] = cmul(a[3 + 12], make_double2(-c1, -SIGN * s1));     // c=3,q=3: W16^9 = -W16^1
+    }
+    // step 3: 4-point DFTs over c for each q: X[q + 4r] = sum_c y'[c][q] W4^(c r)
+#pragma unroll
+    for (int q = 0; q < 4; ++q) bfly4<SIGN>(a[4 * q], a[4 * q + 1], a[4 * q + 2], a[4 * q + 3]);
+    // now a[4q + r] = X[q + 4r]: transpose the 4x4 index block into natural order
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+#pragma unroll
+        for (int r = q + 1; r < 4; ++r) {
+            const double2 t = a[4 * q + r];
+            a[4 * q + r] = a[4 * r + q];
+            a[4 * r + q] = t;
+        }
+}
+
+template <int LOG2N, int SIGN>
+struct RowFft16 {
+    static_assert(LOG2N % 4 == 0, "N must be a power of 16");
+    static constexpr int N = 1 << LOG2N;
+    static constexpr int TPR = N / 16;
+    static constexpr int NB = LOG2N / 4;
+    double2 w16[NB > 1 ? NB - 1 : 1];   // base twiddle of pass p = 1 .. NB-1
+
+    __device__ __forceinline__ void init(const double2* __restrict__ tw, int lt) {
+        int Ns = 16;
+#pragma unroll
+        for (int p = 1; p < NB; ++p) {
+            const int k = lt & (Ns - 1);
+            w16[p - 1] = twid<SIGN>(tw, k * (N / (Ns * 16)));
+            Ns *= 16;
+        }
+    }
+
+    // On entry v[t] = x[lt + t*TPR].  TO_SMEM: on exit the transform sits in `s` (swizzled, natural
+    // order) after a __syncthreads(); otherwise v[u] = X[lt + u*TPR].
+    template <bool TO_SMEM>
+    __device__ __forceinline__ void run(double2 (&v)[16], double2* s, int lt) {
+        int Ns = 1;
+#pragma unroll
+        for (int p = 0; p < NB; ++p) {
+            if (p > 0) {
+                __syncthreads();
+#pragma unroll
+                for (int t = 0; t < 16; ++t) v[t] = s[swz16(lt + t * TPR)];
+                const double2 w1 = w16[p - 1];
+                const double2 w2 = cmul(w1, w1), w3 = cmul(w2, w1), w4 = cmul(w2, w2);
+                v[1] = cmul(v[1], w1);
+                v[2] = cmul(v[2], w2);
+                v[3] = cmul(v[3], w3);
+                v[4] = cmul(v[4], w4);
+                const double2 w5 = cmul(w4, w1), w7 = cmul(w4, w3), w8 = cmul(w4, w4);
+                v[5] = cmul(v[5], w5);
+                v[6] = cmul(v[6], cmul(w3, w3));
+                v[7] = cmul(v[7], w7);
+                v[8] = cmul(v[8], w8);
+                v[9] = cmul(v[9], cmul(w8, w1));
+                v[10] = cmul(v[10], cmul(w8, w2));
+                v[11] = cmul(v[11], cmul(w8, w3));
+                v[12] = cmul(v[12], cmul(w8, w4));
+                v[13] = cmul(v[13], cmul(w8, w5));
+                v[14] = cmul(v[14], cmul(w7, w7));
+                v[15] = cmul(v[15], cmul(w8, w7));
+            }
+            bfly16<SIGN>(v);
+            const bool last = (p == NB - 1);
+            if (!last || TO_SMEM) {
+                if (p > 0) __syncthreads();   // every thread has loaded its inputs of this pass
+                const int k = lt & (Ns - 1);
+                const int j0 = (lt - k) * 16 + k;
+#pragma unroll
+                for (int u = 0; u < 16; ++u) s[swz16(j0 + u * Ns)] = v[u];
+            }
+            Ns *= 16;
+        }
+        if (TO_SMEM) __syncthreads();
+    }
+};
+
+template <int LOG2N>
+struct Fft16Launch {
+    static constexpr int N = 1 << LOG2N;
+    static constexpr int TPR = N / 16;
+    static constexpr int RPB = TPR >= 128 ? 1 : 128 / TPR;
+    static constexpr int THREADS = TPR * RPB;
+    static constexpr int MINB = 2;
+    static constexpr size_t SMEM = (size_t)RPB * N * sizeof(double2);
+};
+
+template <int LOG2N>
+__global__ void __launch_bounds__(Fft16Launch<LOG2N>::THREADS, Fft16Launch<LOG2N>::MINB)
+k2_fft16_forward(const FftArgs a, int ngroups_per_member, int ngroups_total) {
+    using L = Fft16Launch<LOG2N>;
+    using F = RowFft16<LOG2N, -1>;
+    extern __shared__ __align__(16) double2 fft_smem[];
+    constexpr int N = L::N, TPR = L::TPR;
+    const int lr = threadIdx.x / TPR, lt = threadIdx.x % TPR;
+    double2* s = fft_smem + (size_t)lr * N;
+    F fft;
+    fft.init(a.pl.tw, lt);
+    const double A0 = a.A[0], A1 = a.A[1], A2 = a.A[2], A3 = a.A[3];
+
+    for (int grp = blockIdx.x; grp < ngroups_total; grp += gridDim.x) {
+        const int member = grp / ngroups_per_member;
+        const int row = (grp - member * ngroups_per_member) * L::RPB + lr;
+        const bool live = row < a.pl.P;
+        const double* __restrict__ q1 = a.q1 + member * a.mstride + a.g.at(0, live ? row : 0);
+        const double* __restrict__ q2 = a.q2 + member * a.mstride + a.g.at(0, live ? row : 0);
+        double2 v[16];
+#pragma unroll
+        for (int hf = 0; hf < 2; ++hf) {
+            double x1[8], x2[8];
+#pragma unroll
+            for (int t = 0; t < 8; ++t) {
+                x1[t] = __ldg(q1 + lt + (8 * hf + t) * TPR);
+                x2[t] = __ldg(q2 + lt + (8 * hf + t) * TPR);
+            }
+#pragma unroll
+            for (int t = 0; t < 8; ++t)
+                v[8 * hf + t] = make_double2(A0 * x1[t] + A1 * x2[t], A2 * x1[t] + A3 * x2[t]);   // src/model.jl:180
+        }
+        fft.template run<true>(v, s, lt);
+        if (live) {
+            double2* __restrict__ out =
+                reinterpret_cast<double2*>(a.S + member * a.sstride + (int64_t)row * a.pl.ncol);
+            constexpr int half = N >> 1;
+#pragma unroll
+            for (int b = 0; b < 8; ++b) {
+                const int k = lt + b * TPR;   // 0 .. N/2 - 1
+                if (k == 0) {
+                    const double2 z0 = s[swz16(0)];
+                    out[0] = z0;
+                    out[half] = s[swz16(half)];
+                    a.col0[(int64_t)member * a.pl.P + row] = z0.x;   // Q1[0]: the Poisson k=0 column
+                } else {
+                    const double2 X = s[swz16(k)], Y = s[swz16(N - k)];
+                    out[k] = make_double2(0.5 * (X.x + Y.x), 0.5 * (X.y - Y.y));        // Q1[k]
+                    out[N - k] = make_double2(0.5 * (X.y + Y.y), 0.5 * (Y.x - X.x));    // Q2[k]
+                }
+            }
+        }
+        __syncthreads();   // the row buffer is reused by the next group
+    }
+}
+
+template <int LOG2N>
+__global__ void __launch_bounds__(Fft16Launch<LOG2N>::THREADS, Fft16Launch<LOG2N>::MINB)
+k4_fft16_inverse(const FftArgs a, int ngroups_per_member, int ngroups_total) {
+    using L = Fft16Launch<LOG2N>;
+    using F = RowFft16<LOG2N, +1>;
+    extern __shared__ __align__(16) double2 fft_smem[];
+    constexpr int N = L::N, TPR = L::TPR;
+    const int lr = threadIdx.x / TPR, lt = threadIdx.x % TPR;
+    double2* s = fft_smem + (size_t)lr * N;
+    F fft;
+    fft.init(a.pl.tw, lt);
+    const double A0 = a.A[0], A1 = a.A[1], A2 = a.A[2], A3 = a.A[3];
+    const int M = a.g.M, P = a.g.P;
+    const int64_t dyo = (int64_t)P * a.g.pitch;
+    constexpr int half = N >> 1;
+    __shared__ double gsh[32];
+    int gmember = -1;
+    double gauge = 0.0;
+
+    for (int grp = blockIdx.x; grp < ngroups_total; grp += gridDim.x) {
+        const int member = grp / ngroups_per_member;
+        const int row = (grp - member * ngroups_per_member) * L::RPB + lr;
+        const bool live = row < P;
+        if (member != gmember) {   // block-uniform
+            gauge = load_gauge(a, member, gsh);
+            gmember = member;
+        }
+        const double2* __restrict__ in =
+            reinterpret_cast<const double2*>(a.S + member * a.sstride + (int64_t)(live ? row : 0) * a.pl.ncol);
+        double2 v[16];   // see k4_fft_inverse for the re-tangling
+#pragma unroll
+        for (int t = 0; t < 16; ++t) {
+            const int k = lt + t * TPR;
+            if (k == 0 || k == half) {
+                v[t] = __ldg(in + k);
+            } else {
+                const double2 X = __ldg(in + k), Y = __ldg(in + N - k);
+                v[t] = (k < half) ? make_double2(X.x - Y.y, X.y + Y.x) : make_double2(Y.x + X.y, X.x - Y.y);
+            }
+        }
+        fft.template run<false>(v, s, lt);
+        if (live) {
+            double* __restrict__ p1 = a.psi1 + member * a.mstride;
+            double* __restrict__ p2 = a.psi2 + member * a.mstride;
+            const bool gb = a.periodic_y && row < GHOST, gt = a.periodic_y && row >= P - GHOST;
+#pragma unroll
+            for (int e = 0; e < 16; ++e) {
+                const int n = lt + e * TPR;
+                const double2 z = v[e];
+                const double t1 = z.x - gauge;            // pinned node: psi~1(0,0) = 0
+                const double o1 = A0 * t1 + A1 * z.y;     // src/model.jl:196
+                const double o2 = A2 * t1 + A3 * z.y;
+                const int64_t o = a.g.at(n, row);
+                const bool gl = n < GHOST, gr = n >= M - GHOST;
+                p1[o] = o1; p2[o] = o2;
+                if (gl) { p1[o + M] = o1; p2[o + M] = o2; }
+                if (gr) { p1[o - M] = o1; p2[o - M] = o2; }
+                if (gb) {
+                    p1[o + dyo] = o1; p2[o + dyo] = o2;
+                    if (gl) { p1[o + dyo + M] = o1; p2[o + dyo + M] = o2; }
+                    if (gr) { p1[o + dyo - M] = o1; p2[o + dyo - M] = o2; }
+                }
+                if (gt) {
+                    p1[o - dyo] = o1; p2[o - dyo] = o2;
+                    if (gl) { p1[o - dyo + M] = o1; p2[o - dyo + M] = o2; }
+                    if (gr) { p1[o - dyo - M] = o1; p2[o - dyo - M] = o2; }
+                }
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// ---------------------------------------------------------------------------------------
 // M = 2N too long for one shared-memory row (M = 16384: 256 KB as a packed complex row).
 // One CTA per (row, modal field) forward / (row, layer) inverse runs a real transform of
 // length M as a complex transform of length N = M/2 on z[n] = x[2n] + i x[2n+1] plus the
@@ -672,6 +918,30 @@ static cudaError_t launch_pow2(Handle* h, const FftArgs& a) {
 }
 
 template <int LOG2N, bool FWD>
+static cudaError_t launch_r16(Handle* h, const FftArgs& a) {
+    using L = Fft16Launch<LOG2N>;
+    auto kern = FWD ? k2_fft16_forward<LOG2N> : k4_fft16_inverse<LOG2N>;
+    static bool configured = false;
+    static int blocks_per_sm = 1;
+    if (!configured) {
+        if (L::SMEM > 48 * 1024) {
+            cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::SMEM);
+            if (e != cudaSuccess) return e;
+        }
+        cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, kern, L::THREADS, L::SMEM);
+        if (e != cudaSuccess) return e;
+        if (blocks_per_sm < 1) blocks_per_sm = 1;
+        configured = true;
+    }
+    const int gpm = (h->plan.P + L::RPB - 1) / L::RPB;
+    const int total = gpm * h->nm;
+    int grid = num_sms() * blocks_per_sm;
+    if (grid > total) grid = total;
+    kern<<<grid, L::THREADS, L::SMEM, h->stream>>>(a, gpm, total);
+    return cudaGetLastError();
+}
+
+template <int LOG2N, bool FWD>
 static cudaError_t launch_long(Handle* h, const FftArgs& a) {
     using L = FftLaunch<LOG2N>;
     auto kern = FWD ? k2_rfft_forward<LOG2N> : k4_rfft_inverse<LOG2N>;
@@ -695,6 +965,11 @@ static cudaError_t launch_long(Handle* h, const FftArgs& a) {
 
 template <bool FWD>
 static cudaError_t dispatch_pow2(Handle* h, const FftArgs& a) {
+    static const bool radix8_only = getenv("QG_FFT_RADIX8") != nullptr;
+    if (!radix8_only) {
+        if (h->plan.log2M == 12) return launch_r16<12, FWD>(h, a);
+        if (h->plan.log2M == 8) return launch_r16<8, FWD>(h, a);
+    }
     switch (h->plan.log2M) {
         case 3: return launch_pow2<3, FWD>(h, a);
         case 4: return launch_pow2<4, FWD>(h, a);

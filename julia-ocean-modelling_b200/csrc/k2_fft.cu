@@ -489,7 +489,7 @@ struct Fft16Launch {
 
 template <int LOG2N>
 __global__ void __launch_bounds__(Fft16Launch<LOG2N>::THREADS, Fft16Launch<LOG2N>::MINB)
-k2_fft16_forward(const FftArgs a, int ngroups_per_member, int ngroups_total) {
+k2_fft16_forward(const FftArgs a, int ngroups_per_member, int ngroups_total, int pf) {
     using L = Fft16Launch<LOG2N>;
     using F = RowFft16<LOG2N, -1>;
     extern __shared__ __align__(16) double2 fft_smem[];
@@ -519,6 +519,15 @@ k2_fft16_forward(const FftArgs a, int ngroups_per_member, int ngroups_total) {
             for (int t = 0; t < 8; ++t)
                 v[8 * hf + t] = make_double2(A0 * x1[t] + A1 * x2[t], A2 * x1[t] + A3 * x2[t]);   // src/model.jl:180
         }
+        if (pf) {   // this CTA's next row group -> L2 (two resident CTAs of 8 warps cannot hide DRAM latency)
+            const int gn = grp + gridDim.x;
+            if (gn < ngroups_total) {
+                const int mn = gn / ngroups_per_member;
+                const int rn = min((gn - mn * ngroups_per_member) * L::RPB + lr, a.pl.P - 1);
+                prefetch_row_l2(a.q1 + mn * a.mstride + a.g.at(0, rn), N * 8, lt, TPR);
+                prefetch_row_l2(a.q2 + mn * a.mstride + a.g.at(0, rn), N * 8, lt, TPR);
+            }
+        }
         fft.template run<true>(v, s, lt);
         if (live) {
             double2* __restrict__ out =
@@ -545,7 +554,7 @@ k2_fft16_forward(const FftArgs a, int ngroups_per_member, int ngroups_total) {
 
 template <int LOG2N>
 __global__ void __launch_bounds__(Fft16Launch<LOG2N>::THREADS, Fft16Launch<LOG2N>::MINB)
-k4_fft16_inverse(const FftArgs a, int ngroups_per_member, int ngroups_total) {
+k4_fft16_inverse(const FftArgs a, int ngroups_per_member, int ngroups_total, int pf) {
     using L = Fft16Launch<LOG2N>;
     using F = RowFft16<LOG2N, +1>;
     extern __shared__ __align__(16) double2 fft_smem[];
@@ -581,6 +590,14 @@ k4_fft16_inverse(const FftArgs a, int ngroups_per_member, int ngroups_total) {
             } else {
                 const double2 X = __ldg(in + k), Y = __ldg(in + N - k);
                 v[t] = (k < half) ? make_double2(X.x - Y.y, X.y + Y.x) : make_double2(Y.x + X.y, X.x - Y.y);
+            }
+        }
+        if (pf) {   // this CTA's next spectral row(s) -> L2
+            const int gn = grp + gridDim.x;
+            if (gn < ngroups_total) {
+                const int mn = gn / ngroups_per_member;
+                const int rn = min((gn - mn * ngroups_per_member) * L::RPB + lr, P - 1);
+                prefetch_row_l2(a.S + mn * a.sstride + (int64_t)rn * a.pl.ncol, N * 16, lt, TPR);
             }
         }
         fft.template run<false>(v, s, lt);
@@ -937,7 +954,8 @@ static cudaError_t launch_r16(Handle* h, const FftArgs& a) {
     const int total = gpm * h->nm;
     int grid = num_sms() * blocks_per_sm;
     if (grid > total) grid = total;
-    kern<<<grid, L::THREADS, L::SMEM, h->stream>>>(a, gpm, total);
+    static const int pf = getenv("QG_FFT_PF") ? atoi(getenv("QG_FFT_PF")) : 1;
+    kern<<<grid, L::THREADS, L::SMEM, h->stream>>>(a, gpm, total, pf);
     return cudaGetLastError();
 }
 

@@ -624,6 +624,70 @@ __device__ __forceinline__ void st_async_2(uint32_t raddr, double x, double y, u
                  : "memory");
 }
 
+// The singular k = 0 Poisson column inside the persistent kernel (same algorithm as k3_pre, one
+// 256-thread CTA, up to 16 rows per thread): writes the solved column straight into column 0 of
+// the spectral array, so no separate launch sits between K2 and K3.  Block-uniform call.
+__device__ __forceinline__ void k0_column_solve(const YArgs& a, int member, double* sh) {
+    constexpr int E = 16;
+    const int P = a.pl.P;
+    const int e = (P + TP_THREADS - 1) / TP_THREADS;
+    const double* __restrict__ col = a.col0 + (int64_t)member * P;
+    const int j0 = threadIdx.x * e;
+    double b[E];
+    double loc = 0.0;
+#pragma unroll
+    for (int i = 0; i < E; ++i) {
+        const int j = j0 + i;
+        b[i] = (i < e && j < P) ? __ldcg(col + j) : 0.0;
+        loc += b[i];
+    }
+    const double total = block_sum(loc, sh);
+    const double pin = a.pinned ? total : 0.0;
+    const double mean = a.pinned ? 0.0 : total / P;
+    double run = 0.0;
+#pragma unroll
+    for (int i = 0; i < E; ++i) {
+        const int j = j0 + i;
+        double g = 0.0;
+        if (i < e && j < P) g = (b[i] - (j == 0 ? pin : 0.0) - mean) * a.pl.k0scale;
+        run += g;
+        b[i] = run;   // local inclusive prefix
+    }
+    const double off1 = block_exclusive_scan(run, sh);
+    double s1 = 0.0;
+#pragma unroll
+    for (int i = 0; i < E; ++i) {
+        const int j = j0 + i;
+        b[i] += off1;
+        if (i < e && j < P) s1 += b[i];
+    }
+    const double dm1 = -block_sum(s1, sh) / P;
+    double run2 = 0.0;
+#pragma unroll
+    for (int i = 0; i < E; ++i) {
+        const int j = j0 + i;
+        const double x = run2;   // exclusive within the thread
+        if (i < e && j < P) run2 += dm1 + b[i];
+        b[i] = x;
+    }
+    const double off2 = block_exclusive_scan(run2, sh);
+    double* __restrict__ out = a.S + member * a.sstride;
+#pragma unroll
+    for (int i = 0; i < E; ++i) {
+        const int j = j0 + i;
+        if (i < e && j < P) out[(int64_t)j * a.pl.ncol] = b[i] + off2;
+    }
+}
+
+// sum of the k = 0 Poisson column in a fixed order (the pin's right-hand-side correction)
+__device__ __forceinline__ double k0_column_total(const YArgs& a, int member, double* sh) {
+    const double* __restrict__ col = a.col0 + (int64_t)member * a.pl.P;
+    double loc = 0.0;
+    for (int j = threadIdx.x; j < a.pl.P; j += TP_THREADS) loc += __ldcg(col + j);
+    return block_sum(loc, sh);
+}
+
+
 #ifdef QG_K3_TRACE
 #define K3_ACC(i) do { if (tid == 0) { const long long now_ = clock64(); acc[i] += now_ - last; last = now_; } } while (0)
 #else
@@ -679,11 +743,23 @@ k3_ysolve_pipe(const __grid_constant__ CUtensorMap tmS, const __grid_constant__ 
     }
     cluster.sync();   // every CTA's mbarriers exist before anyone pushes to them
 
+    // the k = 0 Poisson columns (one per member) are extra work items at the END of the list, so
+    // they fall to clusters that would otherwise finish one slab early; the slab pass itself
+    // leaves column 0 alone
+    __shared__ double red_sh[32];
+    const int nmember = nwork / nslab;
+    int tot_member = -1;
+    double pinscale = 0.0;
+
 #ifdef QG_K3_TRACE
     long long acc[8] = {0, 0, 0, 0, 0, 0, 0, 0}, last = clock64();
 #endif
     uint32_t it = 0;
-    for (int w = cid; w < nwork; w += ncluster, ++it) {
+    for (int w = cid; w < nwork + nmember; w += ncluster, ++it) {
+        if (w >= nwork) {   // block-uniform
+            if (cr == 0) k0_column_solve(a, w - nwork, red_sh);
+            continue;
+        }
         const int member = w / nslab, slab = w - member * nslab;
         const int col0 = slab * TS_WC;
         const int col = col0 + l;
@@ -691,7 +767,10 @@ k3_ysolve_pipe(const __grid_constant__ CUtensorMap tmS, const __grid_constant__ 
         const double* ct = ctab + (size_t)par * CT_ROWS * TS_WC;
         double* ex = sEx + (size_t)par * 8 * TS_WC * 4;
         uint64_t* xbar = &bar[1 + par];
-        const double pinscale = a.pinned ? a.scal[member * 4 + 0] : 0.0;
+        if (a.pinned && c0 == 0 && a.row0 == 0 && member != tot_member) {   // block-uniform: this CTA owns row 0
+            pinscale = k0_column_total(a, member, red_sh);
+            tot_member = member;
+        }
         if (tid == 0) mbar_expect_tx(xbar, (uint32_t)CS * TS_WC * 4 * sizeof(double));
         K3_ACC(0);
         mbar_wait(&bar[0], par);
@@ -853,16 +932,15 @@ k3_ysolve_pipe(const __grid_constant__ CUtensorMap tmS, const __grid_constant__ 
             const double A = sF[chunk * TS_LD + l], B = sG[chunk * TS_LD + l];
             const double kap = ct[CT_KAP * TS_WC + l];
             const bool cvalid = col < ncol;
-            const double* __restrict__ k0 = a.k0sol + (int64_t)member * a.preP + a.row0 + j0;
+            const bool wr = col < ncol && col != 0;   // column 0 (k = 0 Poisson) is written by k0_column_solve
             double* out = a.S + member * a.sstride + (int64_t)j0 * ncol + (cvalid ? col : 0);
             double u0 = 0.0;
 #pragma unroll
             for (int i = 0; i < 32; ++i) {
-                double u = kap * fma(A, ct[(CT_CA + i) * TS_WC + l], fma(B, ct[(CT_CB + i) * TS_WC + l], v[i]));
-                if (col == 0) u = k0[i];
-                if (cvalid) *out = u;
+                const double u = kap * fma(A, ct[(CT_CA + i) * TS_WC + l], fma(B, ct[(CT_CB + i) * TS_WC + l], v[i]));
+                if (wr) *out = u;
                 out += ncol;
-                if (i == 0) u0 = u;
+                if (i == 0) u0 = u;   // kap = 0 for the singular column: its gauge share is its solved value 0
             }
             // psi~1 at node (0,0) = sum over the x wavenumbers of row 0 of the solved Poisson field:
             // the half-warp that owns global row 0 leaves this slab's share for K4 to add up
@@ -1074,7 +1152,9 @@ cudaError_t launch_ysolve(Handle* h, int pinned, int /*unused*/) {
         a.gpart = h->gpart;
         a.ngp = h->plan.ngp;
     }
-    {
+    static const bool force_v1 = env_int("QG_K3_V1", 0) != 0;
+    const bool pipe = h->plan.ts_ok && h->plan.tp_ok && !force_v1;   // k3_ysolve_pipe solves the k=0 column itself
+    if (!pipe) {
         KernelTimer t(h, QG_K_YPRE);
         launch_pre(a, h->nm, h->stream);
     }

@@ -36,7 +36,7 @@ def gpu_run(mg, zeta, psi, f, first, nsteps):
         s.download(z, p, ff)
         E, Z = s.diagnostics()
         n = s.launch_count()
-    assert n >= 5 * nsteps   # K1, K2, k3_pre, K3, K4 per step
+    assert n >= 4 * nsteps   # K1, K2, K3 (k = 0 column included), K4 per step
     return z, p, ff, E, Z
 
 

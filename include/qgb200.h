@@ -101,6 +101,17 @@ int qg_upload_initial_state(qg_handle* h, const double* zeta, const double* psi)
  * may be NULL. */
 int qg_download_state(qg_handle* h, double* zeta, double* psi, double* f_store);
 
+/* Snapshot of the newest time level only: zeta[:,:,:,1] and psi[:,:,:,1], what run_model
+ * writes at timestep 0 and every sample_timestep (src/run_model.jl:70-73, 86-90).  Host layout
+ * (M+2, P+2, 2) per member, ghosts included; either pointer may be NULL.  qg_snapshot_begin
+ * orders the snapshot after the work already queued on the handle and returns at once: the
+ * device -> host copy runs on its own stream, so steps queued afterwards overlap it.  The host
+ * buffers (pinned memory for a truly asynchronous copy) must stay valid, and must not be read,
+ * until qg_snapshot_end returns.  One snapshot in flight per handle: a second begin waits for
+ * the first. */
+int qg_snapshot_begin(qg_handle* h, double* zeta_level1, double* psi_level1);
+int qg_snapshot_end(qg_handle* h);
+
 /* evolve_zeta!(model, zeta, psi, timestep, f_store), src/model.jl:155-170: Arakawa
  * Jacobian + biharmonic viscosity + beta / mean-flow / friction terms, Euler for
  * timestep 1 and 2, AB3 afterwards; pushes the new RHS into f_store and the new PV into

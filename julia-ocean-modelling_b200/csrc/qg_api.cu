@@ -54,7 +54,7 @@ __global__ void k_unpack(const double* __restrict__ host, double* __restrict__ d
 }
 
 __global__ void k_pack(const double* __restrict__ dev, double* __restrict__ host, Geom g, int nm,
-                       int slot0, int s1, int s2, int y_from_ghost) {
+                       int slot0, int s1, int s2, int y_from_ghost, int hfields) {
     const int ih = blockIdx.x * blockDim.x + threadIdx.x;   // 0 .. M+1 (host index incl. ghost)
     const int jh = blockIdx.y;                              // 0 .. P+1
     if (ih >= g.M + 2) return;
@@ -69,7 +69,8 @@ __global__ void k_pack(const double* __restrict__ dev, double* __restrict__ host
     const int j = y_from_ghost ? jh - 1 : ((jh - 1) % g.P + g.P) % g.P;
     const int64_t hs = (int64_t)(g.M + 2) * (g.P + 2);
     double v = dev[((int64_t)(slot * nm + member) * 2 + layer) * g.fstride + g.at(i, j)];
-    host[(int64_t)member * 6 * hs + (int64_t)(level * 2 + layer) * hs + (int64_t)jh * (g.M + 2) + ih] = v;
+    // hfields = fields per member in the host array: 6 (three levels) or 2 (a snapshot of level 1)
+    host[(int64_t)member * hfields * hs + (int64_t)(level * 2 + layer) * hs + (int64_t)jh * (g.M + 2) + ih] = v;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -483,6 +484,8 @@ int qg_destroy(qg_handle* h) {
     free_plan(h);
     cudaFree(h->col0);
     cudaFree(h->gpart);
+    if (h->copy_stream) { cudaStreamSynchronize(h->copy_stream); cudaStreamDestroy(h->copy_stream); cudaEventDestroy(h->snap_ev); }
+    cudaFree(h->snap_stage);
     cudaFree(h->q); cudaFree(h->psi); cudaFree(h->f); cudaFree(h->S); cudaFree(h->k0sol);
     cudaFree(h->scal); cudaFree(h->stage); cudaFree(h->diag_part);
     for (cudaEvent_t e : h->evpool) cudaEventDestroy(e);
@@ -523,7 +526,7 @@ static int download_one(qg_handle* h, double* dev, double* host, int cur) {
     {
         KernelTimer t(h, QG_K_PACK);
         k_pack<<<grid, block, 0, h->stream>>>(dev, h->stage, h->g, h->nm, cur, (cur + 2) % 3, (cur + 1) % 3,
-                                              h->dist_n > 1 ? 1 : 0);
+                                              h->dist_n > 1 ? 1 : 0, 6);
     }
     QG_CUDA(h, cudaGetLastError());
     QG_CUDA(h, cudaMemcpyAsync(host, h->stage, n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
@@ -596,6 +599,54 @@ int qg_download_state(qg_handle* h, double* zeta, double* psi, double* f_store) 
     if (zeta && (rc = download_one(h, h->q, zeta, h->qcur))) return rc;
     if (psi && (rc = download_one(h, h->psi, psi, h->pcur))) return rc;
     if (f_store && (rc = download_one(h, h->f, f_store, h->qcur))) return rc;
+    return QG_OK;
+}
+
+// Snapshot of the newest level (src/run_model.jl:70-73, 86-90 write exactly zeta[:,:,:,1] and
+// psi[:,:,:,1]): packed on the handle's stream into a staging buffer of its own, copied to the
+// host on a separate stream, so the steps queued after qg_snapshot_begin overlap the PCIe copy.
+int qg_snapshot_end(qg_handle* h) {
+    if (!h) return QG_ERR_INVALID;
+    if (!h->snap_pending) return QG_OK;
+    QG_CUDA(h, cudaSetDevice(h->device));
+    QG_CUDA(h, cudaStreamSynchronize(h->copy_stream));
+    h->snap_pending = false;
+    return QG_OK;
+}
+
+int qg_snapshot_begin(qg_handle* h, double* zeta1, double* psi1) {
+    if (!h || (!zeta1 && !psi1)) return QG_ERR_INVALID;
+    if (!h->have_state) return fail(h, QG_ERR_STATE, "qg_snapshot_begin: no state uploaded");
+    QG_CUDA(h, cudaSetDevice(h->device));
+    int rc = qg_snapshot_end(h);   // the staging buffer is single: finish the previous snapshot first
+    if (rc) return rc;
+    const size_t n = (size_t)h->nm * 2 * (h->g.M + 2) * (h->g.P + 2);
+    if (!h->snap_stage) QG_CUDA(h, cudaMalloc((void**)&h->snap_stage, 2 * n * sizeof(double)));
+    if (!h->copy_stream) {
+        QG_CUDA(h, cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+        QG_CUDA(h, cudaEventCreateWithFlags(&h->snap_ev, cudaEventDisableTiming));
+    }
+    dim3 block(128), grid((h->g.M + 2 + 127) / 128, h->g.P + 2, h->nm * 2);
+    for (int which = 0; which < 2; ++which) {
+        double* host = which == 0 ? zeta1 : psi1;
+        if (!host) continue;
+        double* dev = which == 0 ? h->q : h->psi;
+        const int cur = which == 0 ? h->qcur : h->pcur;
+        if (h->dist_n > 1) QG_CUDA(h, dist_halo_exchange(h, dev, cur));
+        {
+            KernelTimer t(h, QG_K_PACK);
+            k_pack<<<grid, block, 0, h->stream>>>(dev, h->snap_stage + which * n, h->g, h->nm, cur, cur, cur,
+                                                  h->dist_n > 1 ? 1 : 0, 2);
+        }
+        QG_CUDA(h, cudaGetLastError());
+    }
+    QG_CUDA(h, cudaEventRecord(h->snap_ev, h->stream));
+    QG_CUDA(h, cudaStreamWaitEvent(h->copy_stream, h->snap_ev, 0));
+    if (zeta1)
+        QG_CUDA(h, cudaMemcpyAsync(zeta1, h->snap_stage, n * sizeof(double), cudaMemcpyDeviceToHost, h->copy_stream));
+    if (psi1)
+        QG_CUDA(h, cudaMemcpyAsync(psi1, h->snap_stage + n, n * sizeof(double), cudaMemcpyDeviceToHost, h->copy_stream));
+    h->snap_pending = true;
     return QG_OK;
 }
 
@@ -746,7 +797,7 @@ int qg_solve(qg_handle* h, int pinned, const double* f, double* u) {
     if (e == cudaSuccess) {
         dim3 block(128), grid((g.M + 2 + 127) / 128, g.P + 2, 2);
         KernelTimer t(h, QG_K_PACK);
-        k_pack<<<grid, block, 0, h->stream>>>(tmp + 2 * g.fstride, h->stage, g, 1, 0, 0, 0, 0);
+        k_pack<<<grid, block, 0, h->stream>>>(tmp + 2 * g.fstride, h->stage, g, 1, 0, 0, 0, 0, 6);
         e = cudaGetLastError();
     }
     if (e == cudaSuccess)

@@ -163,6 +163,10 @@ struct Handle {
     double* k0sol = nullptr;         // [nm][P]
     double* scal = nullptr;          // [nm][4]
     double* stage = nullptr;         // host-layout staging (3*2*(M+2)*(P+2)*nm doubles)
+    double* snap_stage = nullptr;    // snapshot staging: level 1 of zeta and of psi (qg_snapshot_begin)
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t snap_ev = nullptr;
+    bool snap_pending = false;
     double* col0 = nullptr;          // [nm][P] compact Poisson k=0 column (written by K2)
     double* gpart = nullptr;         // [nm][ngp] gauge partial sums (written by K3, summed by K4)
     // ---- y-slab decomposition of one run over several GPUs (qg_dist_init) ----

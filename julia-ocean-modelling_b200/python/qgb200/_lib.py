@@ -43,6 +43,8 @@ SYMBOLS = {
     "qg_upload_state": (C.c_int, [_P, _P, _P, _P]),
     "qg_upload_initial_state": (C.c_int, [_P, _P, _P]),
     "qg_download_state": (C.c_int, [_P, _P, _P, _P]),
+    "qg_snapshot_begin": (C.c_int, [_P, _P, _P]),
+    "qg_snapshot_end": (C.c_int, [_P]),
     "qg_evolve_zeta": (C.c_int, [_P, C.c_int]),
     "qg_evolve_psi": (C.c_int, [_P]),
     "qg_step": (C.c_int, [_P, C.c_int, C.c_int]),

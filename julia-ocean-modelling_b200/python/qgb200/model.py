@@ -232,6 +232,20 @@ class Session:
                 _as_state(a, self.model, self.members, name)
         self._ck(self._lib.qg_download_state(self._h, self._ptr(zeta), self._ptr(psi), self._ptr(f_store)))
 
+    def snapshot_begin(self, zeta1=None, psi1=None):
+        """Start an asynchronous download of the newest level: ``zeta[:, :, :, 0]`` / ``psi[:, :, :, 0]``
+        as F-ordered ``(M+2, P+2, 2[, members])`` arrays (ideally pinned).  Work queued afterwards
+        overlaps the copy; the arrays are valid after :meth:`snapshot_end`."""
+        shape = (self.model.M + 2, self.model.P + 2, 2) + ((self.members,) if self.members > 1 else ())
+        for name, a in (("zeta1", zeta1), ("psi1", psi1)):
+            if a is not None and not (isinstance(a, np.ndarray) and a.dtype == np.float64 and a.shape == shape
+                                      and a.flags.f_contiguous and a.flags.writeable):
+                raise ValueError(f"{name} must be a writable Fortran-ordered float64 array of shape {shape}")
+        self._ck(self._lib.qg_snapshot_begin(self._h, self._ptr(zeta1), self._ptr(psi1)))
+
+    def snapshot_end(self):
+        self._ck(self._lib.qg_snapshot_end(self._h))
+
     def upload_raw(self, zeta_ptr, psi_ptr, f_ptr):
         """Pointers to host buffers in the reference layout (e.g. pinned torch tensors)."""
         self._ck(self._lib.qg_upload_state(self._h, C.c_void_p(zeta_ptr or 0), C.c_void_p(psi_ptr or 0),

@@ -58,6 +58,9 @@ def test_ten_steps_against_golden(name, golden_dir):
     (40, 24, "direct"), (56, 56, "direct"), (128, 128, "direct"), (128, 100, "spectral"),
     (512, 512, "spectral"), (256, 1100, "spectral"), (1024, 1024, "spectral"), (2048, 96, "spectral"),
     (8192, 64, "spectral"), (64, 4160, "spectral"), (16384, 64, "spectral"),
+    # persistent y-solve with a ragged last CTA: 33 chunks over 4 CTAs of 9 (two 144-row TMA boxes
+    # per tile), 65 chunks over 8 CTAs of 9 (the last CTA owns 2 chunks), and radix-16 rows (M = 256)
+    (256, 1056, "spectral"), (64, 2080, "spectral"), (256, 256, "direct"),
 ])
 def test_ten_steps_against_oracle(M, P, backend):
     """psi, q (and the RHS history) after 10 steps; covers power-of-two and general M,
@@ -272,3 +275,37 @@ def test_initial_upload_and_graph_replay_match_plain_path(monkeypatch):
     assert np.array_equal(za, zb) and np.array_equal(pa, pb) and np.array_equal(fa, fb)
     o.run_steps(mo, zeta, psi, f, o.make_factors(mo, "spectral"), 1, 23)
     assert rel(pa, psi) < TOL_FIELD and rel(za, zeta) < TOL_FIELD
+
+
+@pytest.mark.gpu
+def test_run_model_snapshots_and_restart(tmp_path):
+    """run_model (src/run_model.jl:55-93): the samples written every sample_timestep are the newest
+    level of the trajectory at exactly those steps, the returned arrays equal run_model_no_output's,
+    and a run resumed from a restart file continues bit for bit."""
+    mo, mg = models(64, 64)
+    fn = str(tmp_path / "run.npz")
+    zeta, psi = qgb200.run_model(mg, fn, True, seed=3, sample_timestep=4, total_steps=10)
+    meta, snaps = qgb200.load_run(fn)
+    assert sorted(snaps) == [0, 4, 8] and meta["dt"] == mg.dt
+    zo, po = o.initialise_model(mo, seed=3)
+    fo = np.zeros_like(zo)
+    fac = o.make_factors(mo, "direct")
+    assert np.array_equal(snaps[0][0], zo[:, :, :, 0]) and np.array_equal(snaps[0][1], po[:, :, :, 0])
+    done = 0
+    for t in (4, 8, 10):
+        o.run_steps(mo, zo, po, fo, fac, done + 1, t - done)
+        done = t
+        if t in snaps:
+            assert rel(snaps[t][0], zo[:, :, :, 0]) < TOL_FIELD and rel(snaps[t][1], po[:, :, :, 0]) < TOL_FIELD
+    assert rel(zeta, zo) < TOL_FIELD and rel(psi, po) < TOL_FIELD
+    z2, p2 = qgb200.run_model_no_output(mg, seed=3, total_steps=10)
+    assert np.array_equal(z2, zeta) and np.array_equal(p2, psi)
+    # restart: 6 steps, save, resume 4 more == 10 steps straight
+    zi, pi_ = qgb200.initialise_model(mg, seed=3)
+    rf = str(tmp_path / "restart.npz")
+    with qgb200.Session(mg) as s:
+        s.upload_initial(zi, pi_)
+        s.step(1, 6)
+        qgb200.save_restart(rf, s, 6)
+    z3, p3, f3, t3 = qgb200.resume_model(rf, 4)
+    assert t3 == 10 and np.array_equal(z3, zeta) and np.array_equal(p3, psi)

@@ -110,3 +110,28 @@ def test_plan_tokens_and_argument_checks():
         qgb200.evolve_psi(m, z, z.copy(order="F"), hc, pc)   # swapped plans
     with pytest.raises(ValueError):
         qgb200.evolve_psi(m, z, z.copy(order="F"), pc, qgb200.get_helmholtz_cholesky(16, 16, m.dx, -1.0))
+
+
+def test_run_model_output_container_roundtrip(tmp_path):
+    """The run_model output file (reference keys zeta_<t>, psi_<t>, metadata; src/run_model.jl:6-20,
+    70-73, 86-90) is appended to sample by sample and read back intact; no GPU involved."""
+    from qgb200 import runs as rm
+    m = qgb200.BaroclinicModel(1000.0, 2000.0, 2e-11, 4.0e6, 4.0e6, 3600.0, 10 * 86400.0, 0.1, 8, 8, 5.0e5, 100.0,
+                               1e-7, 4.0e4, 1e-6)
+    meta = rm.create_metadata(m)
+    assert meta == {"dt": 3600.0, "T": 864000.0, "sample_interval": 86400.0, "sample_timestep": 24,
+                    "total_steps": 240}
+    f = str(tmp_path / "run.npz")
+    rng = np.random.default_rng(0)
+    snaps = {t: (rng.random((10, 10, 2)), rng.random((10, 10, 2))) for t in (0, 48, 96)}
+    rm._append(f, zeta_0=snaps[0][0], psi_0=snaps[0][1],
+               metadata=np.frombuffer(__import__("json").dumps(meta).encode(), dtype=np.uint8))
+    for t in (48, 96):
+        rm._append(f, **{f"zeta_{t}": np.asfortranarray(snaps[t][0]), f"psi_{t}": snaps[t][1]})
+    meta2, got = rm.load_run(f)
+    assert meta2 == meta and sorted(got) == [0, 48, 96]
+    for t in snaps:
+        assert np.array_equal(got[t][0], snaps[t][0]) and np.array_equal(got[t][1], snaps[t][1])
+    lines = []
+    rm.log_model_params(m, lines.append)
+    assert lines[0] == "Parameters:" and any(l.startswith("Beta_1 = ") for l in lines) and lines[-1] == "Total steps = 240"

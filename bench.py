@@ -226,6 +226,8 @@ def main():
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--grid", type=int, nargs=2, default=[4096, 4096])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--members", type=int, default=1,
+                    help="ensemble members batched per GPU (BASELINE.json config 5: --grid 512 512 --members 8 on 8 GPUs)")
     ap.add_argument("--mode", default="ensemble", choices=["ensemble", "slab"],
                     help="N > 1: 'ensemble' = one independent run per GPU (default, weak scaling); "
                          "'slab' = ONE run of --grid split into y-slabs over the GPUs (strong scaling)")
@@ -257,7 +259,15 @@ def main():
                                                     "visc", "r", "R_d", "initial_kick")])
     K, W = args.steps, args.warmup
     # synthetic "randomly perturbed jet": seeded white-noise psi on the uniform shear U (rank = member)
-    zeta, psi = qgb200.initialise_model(model, seed=1 + rank)
+    mb = max(1, args.members)
+
+    def initial_state():
+        if mb == 1:
+            return qgb200.initialise_model(model, seed=1 + rank)
+        zs, ps = zip(*[qgb200.initialise_model(model, seed=1 + rank * mb + m) for m in range(mb)])
+        return np.asfortranarray(np.stack(zs, axis=-1)), np.asfortranarray(np.stack(ps, axis=-1))
+
+    zeta, psi = initial_state()
     n_elem = zeta.size
     pin = [torch.empty(n_elem, dtype=torch.float64).pin_memory() for _ in range(3)]
     views = [p.numpy().reshape(zeta.shape, order="F") for p in pin]
@@ -269,7 +279,7 @@ def main():
     # a dedicated (non-default) stream shared by torch's events and the library's launches
     stream = torch.cuda.Stream()
     torch.cuda.set_stream(stream)
-    sess = qgb200.Session(model, members=1, device=local_rank, stream=stream.cuda_stream)
+    sess = qgb200.Session(model, members=mb, device=local_rank, stream=stream.cuda_stream)
 
     def barrier():
         torch.cuda.synchronize()
@@ -302,12 +312,13 @@ def main():
     sampler.stop_flag = True
     sampler.join(timeout=2.0)
     E, Z = sess.diagnostics()
-    if not (np.isfinite(E) and np.isfinite(Z)):
+    E, Z = np.atleast_1d(E), np.atleast_1d(Z)
+    if not (np.all(np.isfinite(E)) and np.all(np.isfinite(Z))):
         raise SystemExit("bench.py: state went non-finite during the timed region")
 
     # ---- end-to-end timing through host buffers ("e2e") -------------------------------------
     views[2][...] = 0.0
-    zeta0, psi0 = qgb200.initialise_model(model, seed=1 + rank)
+    zeta0, psi0 = initial_state()
     views[0][...] = zeta0
     views[1][...] = psi0
     del zeta0, psi0
@@ -329,7 +340,7 @@ def main():
     sess.close()
 
     if rank == 0:
-        cells = float(M) * P
+        cells = float(M) * P * mb      # per GPU
         value = world * cells * K / (ms_total * 1e-3)
         e2e_value = world * cells * Ke / (e2e_ms * 1e-3)
         peak, peak_src = peaks()
@@ -345,11 +356,14 @@ def main():
             "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
             "config": {"workload": f"Phillips two-layer {M}x{P}, Float64, "
-                                   + ("single B200 (BASELINE.json config 3, headline roofline run)" if world == 1 else
+                                   + (f"ensemble of {world * mb} members, {mb} batched per B200 (BASELINE.json config 5 "
+                                      f"shape; member sharding, no collective)" if mb > 1 else
+                                      "single B200 (BASELINE.json config 3, headline roofline run)" if world == 1 else
                                       f"{world} independent members, one per B200 (ensemble sharding, no collective)"),
                        "dt_s": a["dt"], "ic": "seeded uniform psi noise on shear U (initialise_model), seed 1+rank",
-                       "l2": "working set 2.7 GB per GPU >> 126 MB L2, no explicit flush",
-                       "parallelism": f"member-per-gpu x{world}"},
+                       "l2": (f"working set {18 * (M + 18) * (P + 4) * 8 * mb / 1e9 + 16 * M * P * mb / 1e9:.2f} GB per GPU "
+                              f"vs 126 MB L2, no explicit flush"),
+                       "parallelism": f"member-per-gpu x{world}" + (f" ({mb} members per GPU)" if mb > 1 else "")},
             "roofline": {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s",
                          "frac": ach / peak, "traffic": ncu_traffic(dom, M, P), "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": KERNEL_BYTES[dom] * cells,
@@ -365,7 +379,7 @@ def main():
                     "ms_total": e2e_ms},
             "gpu_launches": int(launches),
             "clocks": sampler.result(),
-            "diagnostics": {"E": float(E), "Z": float(Z)},
+            "diagnostics": {"E": float(E[0]), "Z": float(Z[0])},
         }
         if world == 1 and not args.no_cpu_baseline:
             cb, _, _ = cpu_reference_leg(M, P, 4, 1, budget_s=20.0)

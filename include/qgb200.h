@@ -97,6 +97,15 @@ int qg_upload_state(qg_handle* h, const double* zeta, const double* psi, const d
  * src/run_model_no_output.jl:8 hand to the loop.  Moves 4.5x fewer bytes over PCIe. */
 int qg_upload_initial_state(qg_handle* h, const double* zeta, const double* psi);
 
+/* initialise_model (src/model.jl:37-62) on the device, no host arrays involved: psi_l =
+ * amplitude * uniform[0,1) at every node (amplitude = initial_kick * U * Ly, :41-42), periodic
+ * ghosts (:44-45), q_1 = lap(psi_1) + S1 (psi_2 - psi_1), q_2 = lap(psi_2) + S2 (psi_1 - psi_2)
+ * (:47-48) in level 1; history levels and f_store zero.  The reference draws from Julia's
+ * unseeded global RNG; here the stream is Philox4x32-10 with counter (j*M + i, member*2 + layer)
+ * and key `seed`, so a run is reproducible from (seed, parameters) alone.  S1, S2 are
+ * S1_plus / S2_minus of src/model.jl:113-115, evaluated by the host shim. */
+int qg_init_state(qg_handle* h, uint64_t seed, double amplitude, double S1, double S2);
+
 /* Device -> host, all three time levels, ghosts included, reference layout.  Any pointer
  * may be NULL. */
 int qg_download_state(qg_handle* h, double* zeta, double* psi, double* f_store);

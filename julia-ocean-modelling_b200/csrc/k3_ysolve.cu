@@ -1057,7 +1057,8 @@ static cudaError_t launch_tma_kernel(Handle* h, const YArgs& a) {
         if (getenv("QG_VERBOSE")) fprintf(stderr, "qgb200: y-solve persistent clusters: %d x %d CTAs\n", h->plan.tp_ncl, pl.ts_CS);
     }
     const int nwork = nslab * h->nm;
-    const int ncl = h->plan.tp_ncl < nwork ? h->plan.tp_ncl : nwork;
+    // work items = slabs + one k=0 column per member; small grids get clusters of their own for the latter
+    const int ncl = h->plan.tp_ncl < nwork + h->nm ? h->plan.tp_ncl : nwork + h->nm;
     cfg.gridDim = dim3(ncl * pl.ts_CS, 1, 1);
 #ifdef QG_K3_TRACE
     static long long* dbuf = nullptr;

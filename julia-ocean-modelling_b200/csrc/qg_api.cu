@@ -74,6 +74,53 @@ __global__ void k_pack(const double* __restrict__ dev, double* __restrict__ host
 }
 
 // ------------------------------------------------------------------------------------------
+// initial condition on the device (reference src/model.jl:37-62)
+// ------------------------------------------------------------------------------------------
+// Philox4x32-10 (Salmon et al. 2011), counter = (node lo, node hi, field, 0), key = seed: the
+// number at a node depends only on (seed, member, layer, i, j), never on the launch shape.
+__device__ __forceinline__ double philox_uniform(uint64_t node, uint32_t field, uint64_t seed) {
+    uint32_t c0 = (uint32_t)node, c1 = (uint32_t)(node >> 32), c2 = field, c3 = 0u;
+    uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+        const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+        c0 = hi1 ^ c1 ^ k0; c1 = lo1; c2 = hi0 ^ c3 ^ k1; c3 = lo0;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    const uint64_t bits = (((uint64_t)c0 << 32) | c1) >> 11;   // 53 random bits
+    return (double)bits * (1.0 / 9007199254740992.0);          // [0, 1)
+}
+
+// psi_l = amplitude * rand at every interior node (src/model.jl:41-42); the ghost cells get the
+// periodic images (update_doubly_periodic_bc!, :44-45).  One thread per padded device cell.
+__global__ void k_ic_psi(double* __restrict__ psi, Geom g, int nm, double amplitude, uint64_t seed) {
+    const int ix = blockIdx.x * blockDim.x + threadIdx.x - GHOST;
+    const int iy = blockIdx.y - GHOST;
+    if (ix >= g.M + GHOST) return;
+    const int fz = blockIdx.z;   // member * 2 + layer
+    const int i = ((ix % g.M) + g.M) % g.M, j = ((iy % g.P) + g.P) % g.P;
+    const double u = philox_uniform((uint64_t)j * g.M + i, (uint32_t)fz, seed);
+    psi[(int64_t)fz * g.fstride + g.at(ix, iy)] = amplitude * u;
+}
+
+// q1 = lap(psi1) + S1 (psi2 - psi1), q2 = lap(psi2) + S2 (psi1 - psi2)  (src/model.jl:47-48,
+// laplace_5p of src/schemes/laplacian.jl:15-27), ghost images included.
+__global__ void k_ic_q(const double* __restrict__ psi, double* __restrict__ q, Geom g, int nm, double idx2,
+                       double S1, double S2) {
+    const int ix = blockIdx.x * blockDim.x + threadIdx.x - GHOST;
+    const int iy = blockIdx.y - GHOST;
+    if (ix >= g.M + GHOST) return;
+    const int fz = blockIdx.z, layer = fz & 1;
+    const int i = ((ix % g.M) + g.M) % g.M, j = ((iy % g.P) + g.P) % g.P;
+    const double* own = psi + (int64_t)fz * g.fstride;
+    const double* oth = psi + (int64_t)(fz ^ 1) * g.fstride;
+    const int64_t o = g.at(i, j);
+    const double lap = (own[o - 1] + own[o + 1] - 4.0 * own[o] + own[o - g.pitch] + own[o + g.pitch]) * idx2;
+    q[(int64_t)fz * g.fstride + g.at(ix, iy)] = lap + (layer == 0 ? S1 : S2) * (oth[o] - own[o]);
+}
+
+// ------------------------------------------------------------------------------------------
 // diagnostics (DESIGN.md "Diagnostics")
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
@@ -586,6 +633,33 @@ int qg_upload_initial_state(qg_handle* h, const double* zeta, const double* psi)
     if ((rc = upload_level1(h, psi, h->psi))) return rc;
     QG_CUDA(h, cudaMemsetAsync(h->f, 0, (size_t)h->nfields * h->g.fstride * sizeof(double), h->stream));
     QG_CUDA(h, cudaStreamSynchronize(h->stream));
+    h->have_state = true;
+    return QG_OK;
+}
+
+int qg_init_state(qg_handle* h, uint64_t seed, double amplitude, double S1, double S2) {
+    if (!h) return QG_ERR_INVALID;
+    if (h->dist_n > 1) return fail(h, QG_ERR_STATE, "qg_init_state: not available in y-slab mode (upload the slab instead)");
+    QG_CUDA(h, cudaSetDevice(h->device));
+    const size_t bytes = (size_t)h->nfields * h->g.fstride * sizeof(double);
+    QG_CUDA(h, cudaMemsetAsync(h->q, 0, bytes, h->stream));
+    QG_CUDA(h, cudaMemsetAsync(h->psi, 0, bytes, h->stream));
+    QG_CUDA(h, cudaMemsetAsync(h->f, 0, bytes, h->stream));
+    h->qcur = 0;
+    h->pcur = 0;
+    dim3 block(128), grid((h->g.M + 2 * GHOST + 127) / 128, h->g.P + 2 * GHOST, h->nm * 2);
+    const double inv = 1.0 / h->prm.dx;
+    {
+        KernelTimer t(h, QG_K_PACK);
+        k_ic_psi<<<grid, block, 0, h->stream>>>(h->field(h->psi, 0, 0, 0), h->g, h->nm, amplitude, seed);
+    }
+    QG_CUDA(h, cudaGetLastError());
+    {
+        KernelTimer t(h, QG_K_PACK);
+        k_ic_q<<<grid, block, 0, h->stream>>>(h->field(h->psi, 0, 0, 0), h->field(h->q, 0, 0, 0), h->g, h->nm, inv * inv,
+                                              S1, S2);
+    }
+    QG_CUDA(h, cudaGetLastError());
     h->have_state = true;
     return QG_OK;
 }

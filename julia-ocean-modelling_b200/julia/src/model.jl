@@ -132,6 +132,14 @@ qg_step!(h::QGHandle, first_timestep::Integer, nsteps::Integer) = qg_check(h.ptr
 # ---- the reference's API --------------------------------------------------------------------------
 """Initialise the model with a small random psi and then calculate zeta directly
 (reference src/model.jl:37-62; host side, once per run)."""
+"""initialise_model on the device (`qg_init_state`): seeded Philox noise instead of the reference's
+unseeded `rand`, same arithmetic (reference src/model.jl:37-62); nothing crosses PCIe."""
+function initialise_model_device!(h, model::BaroclinicModel, seed::Integer)
+    @assert sign(beta_1(model)) == -sign(beta_2(model))
+    qg_check(h.ptr, ccall((:qg_init_state, libqgb200), Cint, (Ptr{Cvoid}, UInt64, Cdouble, Cdouble, Cdouble),
+                          h.ptr, UInt64(seed), model.initial_kick * model.U * model.Ly, S1_plus(model), S2_minus(model)))
+end
+
 function initialise_model(model::BaroclinicModel)
     @assert sign(beta_1(model)) == -sign(beta_2(model))
     psi_1 = model.initial_kick * model.U * model.Ly * rand(Float64, (model.M+2, model.P+2))

@@ -42,6 +42,7 @@ SYMBOLS = {
     "qg_destroy": (C.c_int, [_P]),
     "qg_upload_state": (C.c_int, [_P, _P, _P, _P]),
     "qg_upload_initial_state": (C.c_int, [_P, _P, _P]),
+    "qg_init_state": (C.c_int, [_P, C.c_uint64, C.c_double, C.c_double, C.c_double]),
     "qg_download_state": (C.c_int, [_P, _P, _P, _P]),
     "qg_snapshot_begin": (C.c_int, [_P, _P, _P]),
     "qg_snapshot_end": (C.c_int, [_P]),

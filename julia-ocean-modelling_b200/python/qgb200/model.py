@@ -232,6 +232,14 @@ class Session:
                 _as_state(a, self.model, self.members, name)
         self._ck(self._lib.qg_download_state(self._h, self._ptr(zeta), self._ptr(psi), self._ptr(f_store)))
 
+    def init_state(self, seed):
+        """initialise_model (src/model.jl:37-62) on the device: seeded Philox noise for psi, q from
+        :47-48, zero history.  Nothing crosses PCIe."""
+        m = self.model
+        assert np.sign(beta_1(m)) == -np.sign(beta_2(m))          # src/model.jl:38
+        self._ck(self._lib.qg_init_state(self._h, C.c_uint64(int(seed)), m.initial_kick * m.U * m.Ly,
+                                         S1_plus(m), S2_minus(m)))
+
     def snapshot_begin(self, zeta1=None, psi1=None):
         """Start an asynchronous download of the newest level: ``zeta[:, :, :, 0]`` / ``psi[:, :, :, 0]``
         as F-ordered ``(M+2, P+2, 2[, members])`` arrays (ideally pinned).  Work queued afterwards
@@ -418,16 +426,21 @@ def evolve_psi(model, zeta, psi, poisson_cholesky, helmholtz_cholesky, device=0)
     s.download(psi=psi)
 
 
-def run_model_no_output(model, seed=None, rand_fields=None, device=0, total_steps=None):
+def run_model_no_output(model, seed=None, rand_fields=None, device=0, total_steps=None, device_ic=None):
     """src/run_model_no_output.jl:3-16: initial condition, plans, ``floor(T/dt)`` steps;
-    returns ``(zeta, psi)``.  State stays in HBM for the whole loop."""
-    zeta, psi = initialise_model(model, seed=seed, rand_fields=rand_fields)
+    returns ``(zeta, psi)``.  State stays in HBM for the whole loop.  ``device_ic=<seed>`` draws
+    the initial condition on the GPU (:meth:`Session.init_state`) instead of on the host."""
     get_poisson_cholesky(model.M, model.P, model.dx)
     get_helmholtz_cholesky(model.M, model.P, model.dx, S_eig(model))
     if total_steps is None:
         total_steps = int(np.floor(model.T / model.dt))
     with Session(model, 1, device) as s:
-        s.upload_initial(zeta, psi)      # f_store = zeros (src/run_model_no_output.jl:8) on the device
+        if device_ic is not None:
+            s.init_state(device_ic)
+            zeta, psi = s.new_state_array(), s.new_state_array()
+        else:
+            zeta, psi = initialise_model(model, seed=seed, rand_fields=rand_fields)
+            s.upload_initial(zeta, psi)  # f_store = zeros (src/run_model_no_output.jl:8) on the device
         s.step(1, total_steps)
         s.download(zeta=zeta, psi=psi)
     return zeta, psi

@@ -309,3 +309,29 @@ def test_run_model_snapshots_and_restart(tmp_path):
         qgb200.save_restart(rf, s, 6)
     z3, p3, f3, t3 = qgb200.resume_model(rf, 4)
     assert t3 == 10 and np.array_equal(z3, zeta) and np.array_equal(p3, psi)
+
+
+@pytest.mark.gpu
+def test_device_initial_condition_matches_host_initialise_model():
+    """qg_init_state == initialise_model (src/model.jl:37-62) fed with the same uniform draws: psi bit
+    for bit (Philox stream restated in tests/philox_ref.py), q to rounding (the device contracts the
+    Laplacian's last multiply-add); history levels and f_store zero; members draw different noise."""
+    import philox_ref
+    mo, mg = models(48, 40)
+    nm = 3
+    with qgb200.Session(mg, members=nm) as s:
+        s.init_state(12345)
+        z, p, f = s.new_state_array(), s.new_state_array(), s.new_state_array()
+        s.download(z, p, f)
+    assert not f.any() and not z[:, :, :, 1:].any() and not p[:, :, :, 1:].any()
+    for m in range(nm):
+        zh, ph = qgb200.initialise_model(mg, rand_fields=philox_ref.rand_fields(48, 40, 12345, member=m))
+        assert np.array_equal(p[..., m], ph)
+        assert rel(z[..., m], zh) < 1e-14
+    assert not np.array_equal(p[..., 0], p[..., 1])
+    u = p[1:-1, 1:-1, :, 0, :] / (mg.initial_kick * mg.U * mg.Ly)
+    assert 0.0 <= u.min() and u.max() < 1.0 and abs(u.mean() - 0.5) < 0.02
+    # and the run it starts is the run the host IC starts
+    za, pa = qgb200.run_model_no_output(mg, device_ic=7, total_steps=5)
+    zb, pb = qgb200.run_model_no_output(mg, rand_fields=philox_ref.rand_fields(48, 40, 7), total_steps=5)
+    assert rel(pa, pb) < TOL_FIELD and rel(za, zb) < TOL_FIELD

@@ -135,3 +135,13 @@ def test_run_model_output_container_roundtrip(tmp_path):
     lines = []
     rm.log_model_params(m, lines.append)
     assert lines[0] == "Parameters:" and any(l.startswith("Beta_1 = ") for l in lines) and lines[-1] == "Total steps = 240"
+
+
+def test_philox_restatement_known_answer():
+    """tests/philox_ref.py (the checker of qg_init_state's random stream) reproduces the published
+    Philox4x32-10 known-answer vector for counter = key = 0 (Random123 kat_vectors)."""
+    import philox_ref
+    w = [int(x[0]) for x in philox_ref.philox_words(np.zeros(1, dtype=np.uint64), 0, 0)]
+    assert w == [0x6627E8D5, 0xE169C58D, 0xBC57AC4C, 0x9B00DBD8]
+    u = philox_ref.philox_uniform(np.arange(200000, dtype=np.uint64), 1, 99)
+    assert 0.0 <= u.min() and u.max() < 1.0 and abs(u.mean() - 0.5) < 5e-3 and abs(u.var() - 1 / 12) < 2e-3

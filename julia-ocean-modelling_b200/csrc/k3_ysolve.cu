@@ -694,6 +694,7 @@ __device__ __forceinline__ double k0_column_total(const YArgs& a, int member, do
 #define K3_ACC(i) do { } while (0)
 #endif
 
+template <int MODE>   // 0: cyclic over the local rows; 1 / 2: y-slab mode, see YArgs::mode
 __global__ void __launch_bounds__(TP_THREADS, 2)
 k3_ysolve_pipe(const __grid_constant__ CUtensorMap tmS, const __grid_constant__ CUtensorMap tmT, const YArgs a,
                int nchunk, int boxrows, int nslab, int nwork) {
@@ -747,7 +748,7 @@ k3_ysolve_pipe(const __grid_constant__ CUtensorMap tmS, const __grid_constant__ 
     // they fall to clusters that would otherwise finish one slab early; the slab pass itself
     // leaves column 0 alone
     __shared__ double red_sh[32];
-    const int nmember = nwork / nslab;
+    const int nmember = MODE == 0 ? nwork / nslab : 0;   // y-slab mode: k3_pre solves the gathered column
     int tot_member = -1;
     double pinscale = 0.0;
 
@@ -768,7 +769,7 @@ k3_ysolve_pipe(const __grid_constant__ CUtensorMap tmS, const __grid_constant__ 
         double* ex = sEx + (size_t)par * 8 * TS_WC * 4;
         uint64_t* xbar = &bar[1 + par];
         if (a.pinned && c0 == 0 && a.row0 == 0 && member != tot_member) {   // block-uniform: this CTA owns row 0
-            pinscale = k0_column_total(a, member, red_sh);
+            pinscale = MODE == 0 ? k0_column_total(a, member, red_sh) : a.scal[member * 4 + 0];
             tot_member = member;
         }
         if (tid == 0) mbar_expect_tx(xbar, (uint32_t)CS * TS_WC * 4 * sizeof(double));
@@ -828,6 +829,12 @@ k3_ysolve_pipe(const __grid_constant__ CUtensorMap tmS, const __grid_constant__ 
             const double rho = act ? ct[CT_RHO * TS_WC + cl] : 1.0;
             const double hh = act ? ct[CT_H * TS_WC + cl] : 0.0;
             const double inv1 = ct[CT_INV1 * TS_WC + cl];
+            double asIn = 0.0, beIn = 0.0;
+            if (MODE == 2) {
+                const int gc = (col0 + cl < ncol) ? col0 + cl : 0;
+                asIn = __ldg(a.Ain + gc);
+                beIn = __ldg(a.Bin + gc);
+            }
             const double F = act ? sF[slot * TS_LD + cl] : 0.0;
             const double G = act ? sG[slot * TS_LD + cl] : 0.0;
             double R = rho, tt = F;
@@ -879,10 +886,28 @@ k3_ysolve_pipe(const __grid_constant__ CUtensorMap tmS, const __grid_constant__ 
                     R1 *= Rp;
                 }
             }
-            // carry into CTA 0: cyclic closure (y at the last row)
-            const double as0 = __shfl_sync(0xffffffffu, T1, 7, 8) * inv1;
             double Rx = __shfl_up_sync(0xffffffffu, R1, 1, 8), Tx = __shfl_up_sync(0xffffffffu, T1, 1, 8);
             if (i8 == 0) { Rx = 1.0; Tx = 0.0; }
+            if (MODE == 1) {
+                // y-slab mode, first kernel: fold the cluster's CTAs into one rank-level aggregate
+                // (same affine composition one level up) and stop; the ranks exchange these.
+                double Xr = Rx * fma(Yl, Tx, Xl), Yr = Rx * (Yl * Rx);
+#pragma unroll
+                for (int d = 4; d > 0; d >>= 1) {
+                    Xr += __shfl_xor_sync(0xffffffffu, Xr, d, 8);
+                    Yr += __shfl_xor_sync(0xffffffffu, Yr, d, 8);
+                }
+                const double Tt = __shfl_sync(0xffffffffu, T1, 7, 8), Rt = __shfl_sync(0xffffffffu, R1, 7, 8);
+                if (cr == 0 && slot == 0 && col0 + cl < ncol) {
+                    a.aggr[0 * ncol + col0 + cl] = Tt;
+                    a.aggr[1 * ncol + col0 + cl] = Rt;
+                    a.aggr[2 * ncol + col0 + cl] = Xr;
+                    a.aggr[3 * ncol + col0 + cl] = Yr;
+                }
+                continue;   // warp-uniform; sF / sG are rewritten only after the next iteration's barrier
+            }
+            // carry into CTA 0: cyclic closure (y at the last row), or handed in by the rank below
+            const double as0 = MODE == 2 ? asIn : __shfl_sync(0xffffffffu, T1, 7, 8) * inv1;
             const double as_i = fma(Rx, as0, Tx);          // forward carry into CTA i
             const double GGp = fma(Yl, as_i, Xl);          // CTA i's backward aggregate with its true carry
             double R2 = RRl, T2 = GGp;   // inclusive backward composition over CTAs 7..i
@@ -895,8 +920,8 @@ k3_ysolve_pipe(const __grid_constant__ CUtensorMap tmS, const __grid_constant__ 
                     R2 *= Rp;
                 }
             }
-            // carry into the last CTA: cyclic closure (z at row 0)
-            const double blast = __shfl_sync(0xffffffffu, T2, 0, 8) * inv1;
+            // carry into the last CTA: cyclic closure (z at row 0), or handed in by the rank above
+            const double blast = MODE == 2 ? beIn : __shfl_sync(0xffffffffu, T2, 0, 8) * inv1;
             Rx = __shfl_down_sync(0xffffffffu, R2, 1, 8);
             Tx = __shfl_down_sync(0xffffffffu, T2, 1, 8);
             if (i8 == 7) { Rx = 1.0; Tx = 0.0; }
@@ -932,12 +957,15 @@ k3_ysolve_pipe(const __grid_constant__ CUtensorMap tmS, const __grid_constant__ 
             const double A = sF[chunk * TS_LD + l], B = sG[chunk * TS_LD + l];
             const double kap = ct[CT_KAP * TS_WC + l];
             const bool cvalid = col < ncol;
-            const bool wr = col < ncol && col != 0;   // column 0 (k = 0 Poisson) is written by k0_column_solve
+            // column 0 (k = 0 Poisson): written by k0_column_solve (mode 0) / taken from k3_pre's solution (mode 2)
+            const bool wr = col < ncol && (MODE != 0 || col != 0);
+            const double* __restrict__ k0 = a.k0sol + (int64_t)member * a.preP + a.row0 + j0;
             double* out = a.S + member * a.sstride + (int64_t)j0 * ncol + (cvalid ? col : 0);
             double u0 = 0.0;
 #pragma unroll
             for (int i = 0; i < 32; ++i) {
-                const double u = kap * fma(A, ct[(CT_CA + i) * TS_WC + l], fma(B, ct[(CT_CB + i) * TS_WC + l], v[i]));
+                double u = kap * fma(A, ct[(CT_CA + i) * TS_WC + l], fma(B, ct[(CT_CB + i) * TS_WC + l], v[i]));
+                if (MODE != 0 && col == 0) u = k0[i];
                 if (wr) *out = u;
                 out += ncol;
                 if (i == 0) u0 = u;   // kap = 0 for the singular column: its gauge share is its solved value 0
@@ -1022,7 +1050,7 @@ static cudaError_t launch_tma_kernel(Handle* h, const YArgs& a) {
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    if (use_v1 || a.mode != 0 || !pl.tp_ok) {
+    if (use_v1 || !pl.tp_ok) {
         cfg.blockDim = dim3(((16 * pl.ts_nchunk + 31) / 32) * 32, 1, 1);
         cfg.dynamicSmemBytes = ((size_t)pl.ts_nchunk * 32 * TS_WC + 32 * TS_WC + 2 * pl.ts_nchunk * TS_LD +
                                 4 * TS_WC) * sizeof(double) + 16;
@@ -1043,22 +1071,25 @@ static cudaError_t launch_tma_kernel(Handle* h, const YArgs& a) {
     cfg.dynamicSmemBytes = ((size_t)pl.ts_nchunk * 32 * TS_WC + 2 * CT_ROWS * TS_WC + 2 * pl.ts_nchunk * TS_LD +
                             2 * 8 * TS_WC * 4) * sizeof(double) + 32;
     if (cfg.dynamicSmemBytes > configured_p) {
-        cudaError_t e = cudaFuncSetAttribute(k3_ysolve_pipe, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             (int)cfg.dynamicSmemBytes);
-        if (e != cudaSuccess) return e;
+        for (auto k : {k3_ysolve_pipe<0>, k3_ysolve_pipe<1>, k3_ysolve_pipe<2>}) {
+            cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cfg.dynamicSmemBytes);
+            if (e != cudaSuccess) return e;
+        }
         configured_p = cfg.dynamicSmemBytes;
     }
+    auto pkern = a.mode == 1 ? k3_ysolve_pipe<1> : (a.mode == 2 ? k3_ysolve_pipe<2> : k3_ysolve_pipe<0>);
     if (h->plan.tp_ncl == 0) {   // clusters the device holds at once
         int ncl = 0;
         cfg.gridDim = dim3(nslab * pl.ts_CS * h->nm, 1, 1);
-        if (cudaOccupancyMaxActiveClusters(&ncl, k3_ysolve_pipe, &cfg) == cudaSuccess && ncl > 0) h->plan.tp_ncl = ncl;
+        if (cudaOccupancyMaxActiveClusters(&ncl, k3_ysolve_pipe<0>, &cfg) == cudaSuccess && ncl > 0) h->plan.tp_ncl = ncl;
         else { h->plan.tp_ncl = 2 * 148 / pl.ts_CS; (void)cudaGetLastError(); }
         if (ncl_env > 0) h->plan.tp_ncl = ncl_env;
         if (getenv("QG_VERBOSE")) fprintf(stderr, "qgb200: y-solve persistent clusters: %d x %d CTAs\n", h->plan.tp_ncl, pl.ts_CS);
     }
     const int nwork = nslab * h->nm;
     // work items = slabs + one k=0 column per member; small grids get clusters of their own for the latter
-    const int ncl = h->plan.tp_ncl < nwork + h->nm ? h->plan.tp_ncl : nwork + h->nm;
+    const int nitems = nwork + (a.mode == 0 ? h->nm : 0);
+    const int ncl = h->plan.tp_ncl < nitems ? h->plan.tp_ncl : nitems;
     cfg.gridDim = dim3(ncl * pl.ts_CS, 1, 1);
 #ifdef QG_K3_TRACE
     static long long* dbuf = nullptr;
@@ -1071,7 +1102,7 @@ static cudaError_t launch_tma_kernel(Handle* h, const YArgs& a) {
     cudaError_t te;
     {
         KernelTimer t(h, QG_K_YSOLVE);
-        te = cudaLaunchKernelEx(&cfg, k3_ysolve_pipe, h->tm_S2, h->tm_T, a, pl.ts_nchunk, pl.tp_boxrows, nslab, nwork);
+        te = cudaLaunchKernelEx(&cfg, pkern, h->tm_S2, h->tm_T, a, pl.ts_nchunk, pl.tp_boxrows, nslab, nwork);
     }
     if (++calls == 20) {
         cudaStreamSynchronize(h->stream);
@@ -1091,7 +1122,7 @@ static cudaError_t launch_tma_kernel(Handle* h, const YArgs& a) {
     return te;
 #else
     KernelTimer t(h, QG_K_YSOLVE);
-    return cudaLaunchKernelEx(&cfg, k3_ysolve_pipe, h->tm_S2, h->tm_T, a, pl.ts_nchunk, pl.tp_boxrows, nslab, nwork);
+    return cudaLaunchKernelEx(&cfg, pkern, h->tm_S2, h->tm_T, a, pl.ts_nchunk, pl.tp_boxrows, nslab, nwork);
 #endif
 }
 

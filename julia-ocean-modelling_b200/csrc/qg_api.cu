@@ -285,7 +285,7 @@ cudaError_t build_plan(Handle* h) {
     // (or two equal ones) per CTA tile, and all per-column constants in one table so that they
     // arrive with the tile:  rows 0-31 cA[i] = r^(i+1) * sum_{m<32-i} r^(2m), rows 32-63
     // cB[i] = r^(32-i), then r, kap, r^32, h32, 1/(1-r^P), pin weight, gauge weight, spare.
-    pl.tp_ok = (pl.ts_ok && P % 32 == 0 && h->dist_n == 1) ? 1 : 0;
+    pl.tp_ok = (pl.ts_ok && P % 32 == 0) ? 1 : 0;
     pl.tp_boxrows = pl.ts_nchunk * 32 <= 256 ? pl.ts_nchunk * 32 : pl.ts_nchunk * 16;
     if (pl.tp_ok) {
         const int NR = 72;
@@ -907,6 +907,7 @@ int qg_dist_init(qg_handle* h, int rank, int nranks, const void* unique_id128) {
     // the cyclic closure now spans the global row count: rebuild the coefficient tables
     free_plan(h);
     QG_CUDA(h, build_plan(h));
+    if (h->plan.ts_ok && (rc = make_tensor_map_S(h))) return rc;   // the column table moved with the plan
     h->have_state = false;
     return QG_OK;
 }

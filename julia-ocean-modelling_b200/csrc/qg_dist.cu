@@ -14,6 +14,7 @@
 #include <dlfcn.h>
 #include <nccl.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "qg_internal.cuh"
@@ -73,11 +74,20 @@ static cudaError_t nccl_check(Handle* h, ncclResult_t r, const char* what) {
     return cudaErrorUnknown;
 }
 
+// Developer diagnostic: QG_DIST_SKIP=<mask> drops collectives (1 halo ring, 2 all-gather, 4 broadcast)
+// to expose their cost in a timing run; results are then wrong by construction.
+static int skip_mask() {
+    static const int m = getenv("QG_DIST_SKIP") ? atoi(getenv("QG_DIST_SKIP")) : 0;
+    return m;
+}
+
 cudaError_t dist_allgather(Handle* h, const double* send, double* recv, size_t count) {
+    if (skip_mask() & 2) return cudaSuccess;
     return nccl_check(h, g_nccl.AllGather(send, recv, count, ncclFloat64, (ncclComm_t)h->nccl, h->stream), "AllGather");
 }
 
 cudaError_t dist_broadcast(Handle* h, double* buf, size_t count, int root) {
+    if (skip_mask() & 4) return cudaSuccess;
     return nccl_check(h, g_nccl.Broadcast(buf, buf, count, ncclFloat64, root, (ncclComm_t)h->nccl, h->stream), "Broadcast");
 }
 
@@ -89,6 +99,7 @@ cudaError_t dist_allreduce_sum(Handle* h, double* buf, size_t count) {
 // neighbours' boundary rows (periodic ring).  Whole padded rows travel, so the x ghosts and the
 // corners arrive with them.
 cudaError_t dist_halo_exchange(Handle* h, double* base, int slot) {
+    if (skip_mask() & 1) return cudaSuccess;
     const Geom& g = h->g;
     const int up = (h->dist_rank + 1) % h->dist_n, down = (h->dist_rank + h->dist_n - 1) % h->dist_n;
     const size_t n = (size_t)GHOST * g.pitch;

@@ -165,6 +165,13 @@ def run_slab(args, rank, world, local_rank, torch, dist, qgb200, np):
     torch.cuda.set_stream(stream)
     sess = qgb200.Session(model, members=1, device=local_rank, stream=stream.cuda_stream)
     sess.dist_init(rank, world, ids[0])
+
+    def gather_blobs(blob):
+        out = [None] * world
+        dist.all_gather_object(out, blob)
+        return out
+
+    sess.dist_peer_init(gather_blobs)   # per-step exchanges over NVLink peer memory (QG_DIST_NCCL=1: stay on NCCL)
     sess.upload(zeta, psi, f)
     del zeta, psi, f
     sess.step(1, W)
@@ -188,6 +195,7 @@ def run_slab(args, rank, world, local_rank, torch, dist, qgb200, np):
     tmax = torch.tensor([ms_total], dtype=torch.float64, device="cuda")
     dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
     ms_total = float(tmax[0])
+    dist.barrier()     # nobody frees memory a peer still has mapped
     sess.close()
     if rank == 0:
         cells = float(M) * P
@@ -202,8 +210,11 @@ def run_slab(args, rank, world, local_rank, torch, dist, qgb200, np):
                 "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
                 "dtype": "f64", "data": "synthetic",
                 "config": {"workload": f"Phillips two-layer {M}x{P}, Float64, ONE run in {world} y-slabs of "
-                                       f"{P // world} rows (BASELINE.json config 4): NCCL send/recv halo ring, "
-                                       f"all-gather of the y-solve carries in place of the all-to-all transpose",
+                                       f"{P // world} rows (BASELINE.json config 4): halo rows, k=0 column and y-solve "
+                                       f"carries exchanged by "
+                                       + ("NCCL send/recv + all-gather" if os.environ.get("QG_DIST_NCCL") else
+                                          "in-kernel NVLink peer stores + flag barriers")
+                                       + " in place of the all-to-all transpose",
                            "dt_s": a["dt"], "parallelism": f"y-slab x{world}",
                            "ic": "per-rank seeded slab (psi noise, q from the slab-periodic Laplacian)"},
                 "roofline": {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s",

@@ -176,6 +176,17 @@ int64_t qg_launch_count(const qg_handle* h);
 int qg_nccl_unique_id(void* out128);
 int qg_dist_init(qg_handle* h, int rank, int nranks, const void* unique_id128);
 
+/* Optional, after qg_dist_init: exchange the per-step data over NVLink peer memory instead of NCCL
+ * calls.  qg_dist_ipc_export fills 192 bytes (three CUDA IPC handles: q, psi, and the rank's
+ * mailbox); the host gathers the exports of all ranks in rank order (nranks x 192 bytes) and hands
+ * them to qg_dist_ipc_import on every rank.  From then on K1 / K4 store their two edge rows
+ * straight into the ring neighbours' ghost rows, K2 its part of the k = 0 column into every
+ * rank's gathered column, the y-solve its carry aggregates into every rank's table, rank 0 the
+ * gauge, and a flag barrier (one tiny kernel, four per step) orders those stores - no collective
+ * call remains on the step path.  Needs peer access between all GPUs of the run (NVSwitch). */
+int qg_dist_ipc_export(qg_handle* h, void* out192);
+int qg_dist_ipc_import(qg_handle* h, const void* all_ranks);
+
 /* Raw device pointers for zero-copy interop (multi-GPU plumbing, torch tensors):
  * which = 0: q, 1: psi, 2: f_store, 3: spectral scratch.  Returns the base pointer, the
  * row pitch in doubles, the left padding (x offset of interior column 0), the ghost-row

@@ -145,20 +145,22 @@ k1_zeta_step(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ C
         // periodic images (update_doubly_periodic_bc!, src/schemes/boundary_conditions.jl:2-13,
         // widened to two ghost cells)
         const bool gl = x < GHOST, gr = x >= a.g.M - GHOST;
-        const bool gb = a.periodic_y && y < GHOST, gt = a.periodic_y && y >= a.g.P - GHOST;
+        const bool gb = a.qimg_lo != nullptr && y < GHOST, gt = a.qimg_hi != nullptr && y >= a.g.P - GHOST;
         if (gl) qn[o + a.g.M] = qnew;
         if (gr) qn[o - a.g.M] = qnew;
-        if (gb | gt) {
+        if (gb | gt) {   // own array (periodic in y) or the ring neighbour's, over NVLink (y-slab mode)
             const int64_t dyo = (int64_t)a.g.P * a.g.pitch;
             if (gb) {
-                qn[o + dyo] = qnew;
-                if (gl) qn[o + dyo + a.g.M] = qnew;
-                if (gr) qn[o + dyo - a.g.M] = qnew;
+                double* __restrict__ im = a.qimg_lo + foff;
+                im[o + dyo] = qnew;
+                if (gl) im[o + dyo + a.g.M] = qnew;
+                if (gr) im[o + dyo - a.g.M] = qnew;
             }
             if (gt) {
-                qn[o - dyo] = qnew;
-                if (gl) qn[o - dyo + a.g.M] = qnew;
-                if (gr) qn[o - dyo - a.g.M] = qnew;
+                double* __restrict__ im = a.qimg_hi + foff;
+                im[o - dyo] = qnew;
+                if (gl) im[o - dyo + a.g.M] = qnew;
+                if (gr) im[o - dyo - a.g.M] = qnew;
             }
         }
         // roll the windows
@@ -194,6 +196,14 @@ cudaError_t launch_zeta(Handle* h, int timestep) {
     a.zpsi = h->zindex(h->pcur, 0, 0);
     a.euler = (timestep == 1 || timestep == 2) ? 1 : 0;   // src/model.jl:161
     a.periodic_y = h->dist_n > 1 ? 0 : 1;
+    a.qimg_lo = a.qimg_hi = nullptr;
+    if (h->dist_n == 1) {
+        a.qimg_lo = a.qimg_hi = a.qn;
+    } else if (h->peer_ok) {   // rows [0,2) -> the rank below, rows [P-2,P) -> the rank above (periodic ring)
+        const int64_t off = a.qn - h->q;
+        a.qimg_lo = h->peer_q[(h->dist_rank + h->dist_n - 1) % h->dist_n] + off;
+        a.qimg_hi = h->peer_q[(h->dist_rank + 1) % h->dist_n] + off;
+    }
     const double inv = 1.0 / h->prm.dx;
     a.idx2 = inv * inv;
     a.hdx = 0.5 * inv;

@@ -47,6 +47,16 @@ __device__ __forceinline__ double2 twid(const double2* __restrict__ tw, int idx)
     return w;
 }
 
+// Q1[0] of one row: the compact k=0 Poisson column.  In y-slab peer mode the value goes straight
+// into every rank's gathered column (NVLink peer stores) instead of a local copy + all-gather.
+__device__ __forceinline__ void store_col0(const FftArgs& a, int member, int row, double v) {
+    if (a.col0_n > 0) {
+        for (int r = 0; r < a.col0_n; ++r) a.col0_peer[r][a.col0_off + row] = v;
+    } else {
+        a.col0[(int64_t)member * a.pl.P + row] = v;
+    }
+}
+
 // bank-conflict-free placement of complex slot i (16-byte elements)
 __device__ __forceinline__ int swz(int i) { return i ^ ((i >> 3) & 7); }
 
@@ -280,7 +290,7 @@ k2_fft_forward(const FftArgs a, int ngroups_per_member, int ngroups_total) {
                     const double2 z0 = s[swz(0)];
                     out[0] = z0;
                     out[half] = s[swz(half)];
-                    a.col0[(int64_t)member * a.pl.P + row] = z0.x;   // Q1[0]: the Poisson k=0 column
+                    store_col0(a, member, row, z0.x);   // Q1[0]: the Poisson k=0 column
                 } else {
                     const double2 X = s[swz(k)], Y = s[swz(N - k)];
                     out[k] = make_double2(0.5 * (X.x + Y.x), 0.5 * (X.y - Y.y));        // Q1[k]
@@ -343,7 +353,12 @@ k4_fft_inverse(const FftArgs a, int ngroups_per_member, int ngroups_total) {
         if (live) {
             double* __restrict__ p1 = a.psi1 + member * a.mstride;
             double* __restrict__ p2 = a.psi2 + member * a.mstride;
-            const bool gb = a.periodic_y && row < GHOST, gt = a.periodic_y && row >= P - GHOST;
+            // images of the edge rows: own array (periodic) or the ring neighbours' (NVLink peer memory)
+            const bool gb = a.pimg_lo != nullptr && row < GHOST, gt = a.pimg_hi != nullptr && row >= P - GHOST;
+            double* __restrict__ lo1 = a.pimg_lo + member * a.mstride;
+            double* __restrict__ lo2 = lo1 + a.g.fstride;
+            double* __restrict__ hi1 = a.pimg_hi + member * a.mstride;
+            double* __restrict__ hi2 = hi1 + a.g.fstride;
 #pragma unroll
             for (int e = 0; e < 8; ++e) {
                 const int n = F::out_index(lt, e);
@@ -357,14 +372,14 @@ k4_fft_inverse(const FftArgs a, int ngroups_per_member, int ngroups_total) {
                 if (gl) { p1[o + M] = o1; p2[o + M] = o2; }
                 if (gr) { p1[o - M] = o1; p2[o - M] = o2; }
                 if (gb) {
-                    p1[o + dyo] = o1; p2[o + dyo] = o2;
-                    if (gl) { p1[o + dyo + M] = o1; p2[o + dyo + M] = o2; }
-                    if (gr) { p1[o + dyo - M] = o1; p2[o + dyo - M] = o2; }
+                    lo1[o + dyo] = o1; lo2[o + dyo] = o2;
+                    if (gl) { lo1[o + dyo + M] = o1; lo2[o + dyo + M] = o2; }
+                    if (gr) { lo1[o + dyo - M] = o1; lo2[o + dyo - M] = o2; }
                 }
                 if (gt) {
-                    p1[o - dyo] = o1; p2[o - dyo] = o2;
-                    if (gl) { p1[o - dyo + M] = o1; p2[o - dyo + M] = o2; }
-                    if (gr) { p1[o - dyo - M] = o1; p2[o - dyo - M] = o2; }
+                    hi1[o - dyo] = o1; hi2[o - dyo] = o2;
+                    if (gl) { hi1[o - dyo + M] = o1; hi2[o - dyo + M] = o2; }
+                    if (gr) { hi1[o - dyo - M] = o1; hi2[o - dyo - M] = o2; }
                 }
             }
         }
@@ -540,7 +555,7 @@ k2_fft16_forward(const FftArgs a, int ngroups_per_member, int ngroups_total, int
                     const double2 z0 = s[swz16(0)];
                     out[0] = z0;
                     out[half] = s[swz16(half)];
-                    a.col0[(int64_t)member * a.pl.P + row] = z0.x;   // Q1[0]: the Poisson k=0 column
+                    store_col0(a, member, row, z0.x);   // Q1[0]: the Poisson k=0 column
                 } else {
                     const double2 X = s[swz16(k)], Y = s[swz16(N - k)];
                     out[k] = make_double2(0.5 * (X.x + Y.x), 0.5 * (X.y - Y.y));        // Q1[k]
@@ -604,7 +619,12 @@ k4_fft16_inverse(const FftArgs a, int ngroups_per_member, int ngroups_total, int
         if (live) {
             double* __restrict__ p1 = a.psi1 + member * a.mstride;
             double* __restrict__ p2 = a.psi2 + member * a.mstride;
-            const bool gb = a.periodic_y && row < GHOST, gt = a.periodic_y && row >= P - GHOST;
+            // images of the edge rows: own array (periodic) or the ring neighbours' (NVLink peer memory)
+            const bool gb = a.pimg_lo != nullptr && row < GHOST, gt = a.pimg_hi != nullptr && row >= P - GHOST;
+            double* __restrict__ lo1 = a.pimg_lo + member * a.mstride;
+            double* __restrict__ lo2 = lo1 + a.g.fstride;
+            double* __restrict__ hi1 = a.pimg_hi + member * a.mstride;
+            double* __restrict__ hi2 = hi1 + a.g.fstride;
 #pragma unroll
             for (int e = 0; e < 16; ++e) {
                 const int n = lt + e * TPR;
@@ -618,14 +638,14 @@ k4_fft16_inverse(const FftArgs a, int ngroups_per_member, int ngroups_total, int
                 if (gl) { p1[o + M] = o1; p2[o + M] = o2; }
                 if (gr) { p1[o - M] = o1; p2[o - M] = o2; }
                 if (gb) {
-                    p1[o + dyo] = o1; p2[o + dyo] = o2;
-                    if (gl) { p1[o + dyo + M] = o1; p2[o + dyo + M] = o2; }
-                    if (gr) { p1[o + dyo - M] = o1; p2[o + dyo - M] = o2; }
+                    lo1[o + dyo] = o1; lo2[o + dyo] = o2;
+                    if (gl) { lo1[o + dyo + M] = o1; lo2[o + dyo + M] = o2; }
+                    if (gr) { lo1[o + dyo - M] = o1; lo2[o + dyo - M] = o2; }
                 }
                 if (gt) {
-                    p1[o - dyo] = o1; p2[o - dyo] = o2;
-                    if (gl) { p1[o - dyo + M] = o1; p2[o - dyo + M] = o2; }
-                    if (gr) { p1[o - dyo - M] = o1; p2[o - dyo - M] = o2; }
+                    hi1[o - dyo] = o1; hi2[o - dyo] = o2;
+                    if (gl) { hi1[o - dyo + M] = o1; hi2[o - dyo + M] = o2; }
+                    if (gr) { hi1[o - dyo - M] = o1; hi2[o - dyo - M] = o2; }
                 }
             }
         }
@@ -707,7 +727,7 @@ k2_rfft_forward(const FftArgs a, int ngroups_per_member, int ngroups_total) {
                 outs[2 * N + field] = Z0.x - Z0.y;          // X[N]  -> slot M/2
                 const double2 Xh = cconj(Zh);               // X[N/2]
                 if (field == 0) out[N / 2] = Xh; else out[M - N / 2] = Xh;
-                if (field == 0) a.col0[(int64_t)member * a.pl.P + row] = Z0.x + Z0.y;
+                if (field == 0) store_col0(a, member, row, Z0.x + Z0.y);
             } else {
                 const double2 Za = s[swz(k)], Zb = s[swz(N - k)];
                 const double2 E = make_double2(0.5 * (Za.x + Zb.x), 0.5 * (Za.y - Zb.y));
@@ -773,7 +793,9 @@ k4_rfft_inverse(const FftArgs a, int ngroups_per_member, int ngroups_total) {
         }
         fft.template run<false>(v, s, lt);
         double* __restrict__ p = (layer == 0 ? a.psi1 : a.psi2) + member * a.mstride;
-        const bool gb = a.periodic_y && row < GHOST, gt = a.periodic_y && row >= P - GHOST;
+        const bool gb = a.pimg_lo != nullptr && row < GHOST, gt = a.pimg_hi != nullptr && row >= P - GHOST;
+        double* __restrict__ plo = a.pimg_lo + member * a.mstride + layer * a.g.fstride;
+        double* __restrict__ phi = a.pimg_hi + member * a.mstride + layer * a.g.fstride;
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
             const int n = F::out_index(lt, e);        // z[n] = (psi[2n], psi[2n+1])
@@ -784,14 +806,14 @@ k4_rfft_inverse(const FftArgs a, int ngroups_per_member, int ngroups_total) {
             if (gl) *reinterpret_cast<double2*>(p + o + M) = z;
             if (gr) *reinterpret_cast<double2*>(p + o - M) = z;
             if (gb) {
-                *reinterpret_cast<double2*>(p + o + dyo) = z;
-                if (gl) *reinterpret_cast<double2*>(p + o + dyo + M) = z;
-                if (gr) *reinterpret_cast<double2*>(p + o + dyo - M) = z;
+                *reinterpret_cast<double2*>(plo + o + dyo) = z;
+                if (gl) *reinterpret_cast<double2*>(plo + o + dyo + M) = z;
+                if (gr) *reinterpret_cast<double2*>(plo + o + dyo - M) = z;
             }
             if (gt) {
-                *reinterpret_cast<double2*>(p + o - dyo) = z;
-                if (gl) *reinterpret_cast<double2*>(p + o - dyo + M) = z;
-                if (gr) *reinterpret_cast<double2*>(p + o - dyo - M) = z;
+                *reinterpret_cast<double2*>(phi + o - dyo) = z;
+                if (gl) *reinterpret_cast<double2*>(phi + o - dyo + M) = z;
+                if (gr) *reinterpret_cast<double2*>(phi + o - dyo - M) = z;
             }
         }
         __syncthreads();
@@ -829,7 +851,7 @@ k2_dft_forward(const FftArgs a) {
     for (int k = threadIdx.x; k <= N / 2; k += blockDim.x) {
         if (k == 0 || 2 * k == N) {
             out[k] = Z[k];
-            if (k == 0) a.col0[(int64_t)member * a.pl.P + row] = Z[0].x;
+            if (k == 0) store_col0(a, member, row, Z[0].x);
         } else {
             const double2 A = Z[k], B = Z[N - k];
             out[k] = make_double2(0.5 * (A.x + B.x), 0.5 * (A.y - B.y));
@@ -873,7 +895,11 @@ k4_dft_inverse(const FftArgs a) {
     double* __restrict__ p2 = a.psi2 + member * a.mstride;
     const int M = a.g.M, P = a.g.P;
     const int64_t dyo = (int64_t)P * a.g.pitch;
-    const bool gb = a.periodic_y && row < GHOST, gt = a.periodic_y && row >= P - GHOST;
+    const bool gb = a.pimg_lo != nullptr && row < GHOST, gt = a.pimg_hi != nullptr && row >= P - GHOST;
+    double* __restrict__ lo1 = a.pimg_lo + member * a.mstride;
+    double* __restrict__ lo2 = lo1 + a.g.fstride;
+    double* __restrict__ hi1 = a.pimg_hi + member * a.mstride;
+    double* __restrict__ hi2 = hi1 + a.g.fstride;
     for (int n = threadIdx.x; n < N; n += blockDim.x) {
         const double t1 = z[n].x - gauge;
         const double o1 = a.A[0] * t1 + a.A[1] * z[n].y;
@@ -884,14 +910,14 @@ k4_dft_inverse(const FftArgs a) {
         if (gl) { p1[o + M] = o1; p2[o + M] = o2; }
         if (gr) { p1[o - M] = o1; p2[o - M] = o2; }
         if (gb) {
-            p1[o + dyo] = o1; p2[o + dyo] = o2;
-            if (gl) { p1[o + dyo + M] = o1; p2[o + dyo + M] = o2; }
-            if (gr) { p1[o + dyo - M] = o1; p2[o + dyo - M] = o2; }
+            lo1[o + dyo] = o1; lo2[o + dyo] = o2;
+            if (gl) { lo1[o + dyo + M] = o1; lo2[o + dyo + M] = o2; }
+            if (gr) { lo1[o + dyo - M] = o1; lo2[o + dyo - M] = o2; }
         }
         if (gt) {
-            p1[o - dyo] = o1; p2[o - dyo] = o2;
-            if (gl) { p1[o - dyo + M] = o1; p2[o - dyo + M] = o2; }
-            if (gr) { p1[o - dyo - M] = o1; p2[o - dyo - M] = o2; }
+            hi1[o - dyo] = o1; hi2[o - dyo] = o2;
+            if (gl) { hi1[o - dyo + M] = o1; hi2[o - dyo + M] = o2; }
+            if (gr) { hi1[o - dyo - M] = o1; hi2[o - dyo - M] = o2; }
         }
     }
 }
@@ -1023,6 +1049,11 @@ cudaError_t launch_fft_forward(Handle* h, const double* q_fields, int /*which*/)
     for (int i = 0; i < 4; ++i) a.A[i] = h->prm.Pinv[i];
     a.scal = h->scal;
     a.col0 = h->col0;
+    if (h->peer_ok) {   // y-slab peer mode: the k=0 column is gathered by the stores themselves
+        a.col0_n = h->dist_n;
+        a.col0_off = h->dist_rank * h->plan.P;
+        for (int r = 0; r < h->dist_n; ++r) a.col0_peer[r] = h->peer_mail[r] + 256;
+    }
     KernelTimer t(h, QG_K_FFT_FWD);
     if (h->plan.pow2) return dispatch_pow2<true>(h, a);
     const size_t smem = 2 * (size_t)h->plan.M * sizeof(double2);
@@ -1046,6 +1077,14 @@ cudaError_t launch_fft_inverse(Handle* h, double* psi_fields, int use_gauge) {
     a.scal = h->scal;
     a.use_gauge = use_gauge;
     a.periodic_y = h->dist_n > 1 ? 0 : 1;
+    if (h->dist_n == 1) {
+        a.pimg_lo = a.pimg_hi = a.psi1;
+    } else if (h->peer_ok && psi_fields >= h->psi && psi_fields < h->psi + (int64_t)h->nfields * h->g.fstride) {
+        // rows [0,2) -> the rank below, rows [P-2,P) -> the rank above (periodic ring)
+        const int64_t off = a.psi1 - h->psi;
+        a.pimg_lo = h->peer_psi[(h->dist_rank + h->dist_n - 1) % h->dist_n] + off;
+        a.pimg_hi = h->peer_psi[(h->dist_rank + 1) % h->dist_n] + off;
+    }
     if (h->plan.ts_ok && h->dist_n == 1) {   // K3 left per-slab shares of the gauge instead of running k3_gauge
         a.gpart = h->gpart;
         a.ngp = h->plan.ngp;

@@ -124,6 +124,7 @@ __global__ void __launch_bounds__(256) k3_gauge(const YArgs a) {
         t += row0[0];
         if ((M & 1) == 0) t += row0[M];
         a.scal[member * 4 + 1] = t;
+        for (int r = 0; r < a.peer_n; ++r) a.scal_peer[r][member * 4 + 1] = t;   // y-slab peer mode: every rank's copy
     }
 }
 
@@ -904,6 +905,14 @@ k3_ysolve_pipe(const __grid_constant__ CUtensorMap tmS, const __grid_constant__ 
                     a.aggr[2 * ncol + col0 + cl] = Xr;
                     a.aggr[3 * ncol + col0 + cl] = Yr;
                 }
+                // peer mode: lane r of the half-warp pushes the aggregate into rank r's aggr_all[this rank]
+                if (cr == 0 && slot < a.peer_n && col0 + cl < ncol) {
+                    double* dst = a.aggr_peer[slot] + (size_t)a.peer_rank * 4 * ncol + col0 + cl;
+                    dst[0] = Tt;
+                    dst[ncol] = Rt;
+                    dst[2 * ncol] = Xr;
+                    dst[3 * ncol] = Yr;
+                }
                 continue;   // warp-uniform; sF / sG are rewritten only after the next iteration's barrier
             }
             // carry into CTA 0: cyclic closure (y at the last row), or handed in by the rank below
@@ -1142,7 +1151,18 @@ static cudaError_t launch_ysolve_dist(Handle* h, int pinned) {
     a.aggr = h->aggr;
     a.Ain = h->carry_in;
     a.Bin = h->carry_in + h->plan.ncol;
-    cudaError_t e = dist_allgather(h, h->col0, h->col0_full, (size_t)h->plan.P);
+    static const bool force_v1 = env_int("QG_K3_V1", 0) != 0;
+    const bool peer = h->peer_ok && h->plan.tp_ok && !force_v1;   // exchanges by in-kernel peer stores + flag barriers
+    if (peer) {
+        a.peer_n = h->dist_n;
+        a.peer_rank = h->dist_rank;
+        for (int r = 0; r < h->dist_n; ++r) {
+            a.aggr_peer[r] = h->peer_mail[r] + (h->aggr_all - h->mailbox);
+            a.scal_peer[r] = h->peer_mail[r] + (h->scal - h->mailbox);
+        }
+    }
+    // K2 has written the k=0 column: gathered by NCCL, or already in place on every rank (peer stores)
+    cudaError_t e = peer ? dist_barrier(h) : dist_allgather(h, h->col0, h->col0_full, (size_t)h->plan.P);
     if (e != cudaSuccess) return e;
     {
         KernelTimer t(h, QG_K_YPRE);
@@ -1151,7 +1171,8 @@ static cudaError_t launch_ysolve_dist(Handle* h, int pinned) {
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
     a.mode = 1;
     if ((e = launch_tma_kernel(h, a)) != cudaSuccess) return e;
-    if ((e = dist_allgather(h, h->aggr, h->aggr_all, (size_t)4 * h->plan.ncol)) != cudaSuccess) return e;
+    e = peer ? dist_barrier(h) : dist_allgather(h, h->aggr, h->aggr_all, (size_t)4 * h->plan.ncol);
+    if (e != cudaSuccess) return e;
     {
         KernelTimer t(h, QG_K_GAUGE);
         k3_rank_closure<<<(h->plan.ncol + 255) / 256, 256, 0, h->stream>>>(
@@ -1166,7 +1187,7 @@ static cudaError_t launch_ysolve_dist(Handle* h, int pinned) {
         k3_gauge<<<1, 256, 0, h->stream>>>(a);
         if ((e = cudaGetLastError()) != cudaSuccess) return e;
     }
-    return dist_broadcast(h, h->scal, 4, 0);
+    return peer ? dist_barrier(h) : dist_broadcast(h, h->scal, 4, 0);
 }
 
 cudaError_t launch_ysolve(Handle* h, int pinned, int /*unused*/) {

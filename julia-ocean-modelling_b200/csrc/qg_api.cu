@@ -414,13 +414,17 @@ static int do_evolve_psi(Handle* h) {
     QG_CUDA(h, launch_ysolve(h, 1, 0));
     QG_CUDA(h, launch_fft_inverse(h, h->field(h->psi, nxt, 0, 0), 1));
     h->pcur = nxt;
-    if (h->dist_n > 1) QG_CUDA(h, dist_halo_exchange(h, h->psi, nxt));
+    // y-slab: psi's ghost rows come from the ring neighbours - NCCL send/recv, or (peer mode) K4 has
+    // stored them itself and the barrier orders those stores (and K1's q rows) before the next step
+    if (h->dist_n > 1) QG_CUDA(h, h->peer_ok ? dist_barrier(h) : dist_halo_exchange(h, h->psi, nxt));
     return QG_OK;
 }
 
 static int do_evolve_zeta(Handle* h, int timestep) {
     QG_CUDA(h, launch_zeta(h, timestep));
-    if (h->dist_n > 1) QG_CUDA(h, dist_halo_exchange(h, h->q, h->qcur));
+    // peer mode: K1 stored its edge rows into the neighbours' ghost rows; they are read by the next
+    // step's K1 only, after the barriers of evolve_psi
+    if (h->dist_n > 1 && !h->peer_ok) QG_CUDA(h, dist_halo_exchange(h, h->q, h->qcur));
     return QG_OK;
 }
 
@@ -910,6 +914,19 @@ int qg_dist_init(qg_handle* h, int rank, int nranks, const void* unique_id128) {
     if (h->plan.ts_ok && (rc = make_tensor_map_S(h))) return rc;   // the column table moved with the plan
     h->have_state = false;
     return QG_OK;
+}
+
+int qg_dist_ipc_export(qg_handle* h, void* out192) {
+    if (!h || !out192) return QG_ERR_INVALID;
+    QG_CUDA(h, cudaSetDevice(h->device));
+    return dist_ipc_export(h, out192);
+}
+
+int qg_dist_ipc_import(qg_handle* h, const void* all_ranks) {
+    if (!h || !all_ranks) return QG_ERR_INVALID;
+    if (getenv("QG_DIST_NCCL") || getenv("QG_K3_V1")) return QG_OK;   // diagnostics: stay on the NCCL path
+    QG_CUDA(h, cudaSetDevice(h->device));
+    return dist_ipc_import(h, all_ranks);
 }
 
 int qg_set_profiling(qg_handle* h, int enabled) {

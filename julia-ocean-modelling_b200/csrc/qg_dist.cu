@@ -122,11 +122,95 @@ cudaError_t dist_halo_exchange(Handle* h, double* base, int slot) {
     return nccl_check(h, r2, "GroupEnd");
 }
 
+// ---- peer-memory exchange ----------------------------------------------------------------------
+// One process per GPU, so the other ranks' arrays are reached through CUDA IPC handles; NVSwitch
+// gives every pair full NVLink bandwidth.  Producers store straight into the consumers' memory
+// (K1 / K4: two halo rows into each ring neighbour's ghost rows; K2: its part of the k=0 column
+// into every rank's gathered column; y-solve mode 1: its carry aggregates into every rank's
+// aggr_all; rank 0: the gauge) and the ranks order these stores with a flag barrier:
+// rank r writes the barrier's epoch into slot r of every rank's flag array (st.release.sys after a
+// system-scope fence) and spins until all slots of its own array carry that epoch.  Kernels on
+// a stream run in order, so a rank signals only after its producing kernel has completed, and
+// its consumer starts only after everyone has signalled.
+struct PeerFlags {
+    unsigned long long* f[8];
+};
+
+__global__ void k_xgpu_barrier(PeerFlags p, int rank, int n, unsigned long long epoch) {
+    const int i = threadIdx.x;
+    if (i < n) {
+        __threadfence_system();
+        asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p.f[i] + rank * 16), "l"(epoch) : "memory");
+        unsigned long long v;
+        do {
+            asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p.f[rank] + i * 16) : "memory");
+        } while (v < epoch);
+    }
+}
+
+cudaError_t dist_barrier(Handle* h) {
+    PeerFlags p{};
+    for (int r = 0; r < h->dist_n; ++r) p.f[r] = reinterpret_cast<unsigned long long*>(h->peer_mail[r]);
+    ++h->epoch;
+    h->launches++;
+    k_xgpu_barrier<<<1, 32, 0, h->stream>>>(p, h->dist_rank, h->dist_n, h->epoch);
+    return cudaGetLastError();
+}
+
+int dist_ipc_export(Handle* h, void* out192) {
+    if (h->dist_n < 2 || !h->mailbox) { h->err = "qg_dist_ipc_export: call qg_dist_init first"; return QG_ERR_STATE; }
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+    cudaIpcMemHandle_t hd[3];
+    void* ptr[3] = {h->q, h->psi, h->mailbox};
+    for (int i = 0; i < 3; ++i) {
+        cudaError_t e = cudaIpcGetMemHandle(&hd[i], ptr[i]);
+        if (e != cudaSuccess) { h->err = std::string("cudaIpcGetMemHandle: ") + cudaGetErrorString(e); return QG_ERR_CUDA; }
+    }
+    memcpy(out192, hd, sizeof(hd));
+    return QG_OK;
+}
+
+int dist_ipc_import(Handle* h, const void* all) {
+    if (h->dist_n < 2 || !h->mailbox) { h->err = "qg_dist_ipc_import: call qg_dist_init first"; return QG_ERR_STATE; }
+    if (h->peer_ok) return QG_OK;
+    const cudaIpcMemHandle_t* hd = static_cast<const cudaIpcMemHandle_t*>(all);
+    for (int r = 0; r < h->dist_n; ++r) {
+        if (r == h->dist_rank) {
+            h->peer_q[r] = h->q; h->peer_psi[r] = h->psi; h->peer_mail[r] = h->mailbox;
+            continue;
+        }
+        double** dst[3] = {&h->peer_q[r], &h->peer_psi[r], &h->peer_mail[r]};
+        for (int i = 0; i < 3; ++i) {
+            void* p = nullptr;
+            cudaError_t e = cudaIpcOpenMemHandle(&p, hd[3 * r + i], cudaIpcMemLazyEnablePeerAccess);
+            if (e != cudaSuccess) {
+                h->err = std::string("cudaIpcOpenMemHandle (is NVLink peer access available?): ") + cudaGetErrorString(e);
+                return QG_ERR_CUDA;
+            }
+            *dst[i] = static_cast<double*>(p);
+        }
+    }
+    h->peer_ok = true;
+    if (getenv("QG_VERBOSE"))
+        fprintf(stderr, "qgb200: rank %d/%d exchanges over NVLink peer memory (CUDA IPC), NCCL off the step path\n",
+                h->dist_rank, h->dist_n);
+    return QG_OK;
+}
+
 void dist_destroy(Handle* h) {
+    if (h->peer_ok) {
+        cudaStreamSynchronize(h->stream);
+        for (int r = 0; r < h->dist_n; ++r)
+            if (r != h->dist_rank) {
+                cudaIpcCloseMemHandle(h->peer_q[r]); cudaIpcCloseMemHandle(h->peer_psi[r]); cudaIpcCloseMemHandle(h->peer_mail[r]);
+            }
+        h->peer_ok = false;
+    }
     if (h->nccl && g_nccl.CommDestroy) g_nccl.CommDestroy((ncclComm_t)h->nccl);
     h->nccl = nullptr;
-    cudaFree(h->col0_full); cudaFree(h->k0sol_full); cudaFree(h->aggr); cudaFree(h->aggr_all); cudaFree(h->carry_in);
-    h->col0_full = h->k0sol_full = h->aggr = h->aggr_all = h->carry_in = nullptr;
+    if (h->own_scal) { h->scal = h->own_scal; h->own_scal = nullptr; }
+    cudaFree(h->mailbox); cudaFree(h->k0sol_full); cudaFree(h->aggr); cudaFree(h->carry_in);
+    h->mailbox = h->col0_full = h->k0sol_full = h->aggr = h->aggr_all = h->carry_in = nullptr;
 }
 
 int dist_unique_id(void* out128, std::string* err) {
@@ -153,12 +237,22 @@ int dist_init(Handle* h, int rank, int nranks, const void* id128) {
     h->dist_rank = rank;
     h->Pglob = h->g.P * nranks;
     const size_t ncol = h->plan.ncol;
-    cudaError_t ce = cudaMalloc((void**)&h->col0_full, (size_t)h->Pglob * sizeof(double));
+    // everything another rank may write lives in one allocation (one IPC handle): barrier flags,
+    // the gathered k=0 column, every rank's carry aggregates, the scalars (pin total, gauge)
+    const size_t pg = ((size_t)h->Pglob + 15) / 16 * 16;
+    h->mailbox_doubles = 256 + pg + (size_t)nranks * 4 * ncol + 16;
+    cudaError_t ce = cudaMalloc((void**)&h->mailbox, h->mailbox_doubles * sizeof(double));
+    if (ce == cudaSuccess) ce = cudaMemset(h->mailbox, 0, h->mailbox_doubles * sizeof(double));
     if (ce == cudaSuccess) ce = cudaMalloc((void**)&h->k0sol_full, (size_t)h->Pglob * sizeof(double));
     if (ce == cudaSuccess) ce = cudaMalloc((void**)&h->aggr, 4 * ncol * sizeof(double));
-    if (ce == cudaSuccess) ce = cudaMalloc((void**)&h->aggr_all, (size_t)nranks * 4 * ncol * sizeof(double));
     if (ce == cudaSuccess) ce = cudaMalloc((void**)&h->carry_in, 2 * ncol * sizeof(double));
+    if (ce == cudaSuccess) ce = cudaDeviceSynchronize();
     if (ce != cudaSuccess) { h->err = std::string("qg_dist_init: ") + cudaGetErrorString(ce); return QG_ERR_NOMEM; }
+    h->col0_full = h->mailbox + 256;
+    h->aggr_all = h->col0_full + pg;
+    h->own_scal = h->scal;
+    h->scal = h->aggr_all + (size_t)nranks * 4 * ncol;
+    h->epoch = 0;
     return QG_OK;
 }
 

@@ -46,6 +46,11 @@ struct ZetaArgs {
     int zq, zpsi;       // first field index (tensor-map z coordinate) of q / psi inputs
     int euler;          // 1: steps 1-2 (no history read)
     int periodic_y;     // 1: write the y ghost images locally; 0: y-slab mode
+    // Where the images of the first / last GHOST rows of q+ go (field 0 of the output slot, same
+    // layout): this rank's own array when the run is periodic in y on one GPU, the ring
+    // neighbours' arrays (NVLink peer memory) in y-slab mode, nullptr when NCCL fills the ghosts.
+    double* qimg_lo;    // receives rows [0, GHOST) as its rows [P, P+GHOST)
+    double* qimg_hi;    // receives rows [P-GHOST, P) as its rows [-GHOST, 0)
     double idx2;        // (1/dx)^2
     double hdx;         // 0.5*(1/dx)
     double i12dx2;      // 1 / (3*4*dx^2)
@@ -91,6 +96,10 @@ struct FftArgs {
     const double* scal;  // per member: [0] = sum of the Poisson k=0 column, [1] = gauge
     int use_gauge;
     int periodic_y;      // 1: write the y ghost images locally; 0: y-slab mode (halo exchange fills them)
+    double* pimg_lo;     // inverse: where the images of the first / last GHOST rows of psi go (layer-1 field
+    double* pimg_hi;     // of the output slot): own array, ring neighbours' peer memory, or nullptr (NCCL)
+    double* col0_peer[8];   // forward, y-slab peer mode: every rank's gathered k=0 column; col0_n = 0 otherwise
+    int col0_n, col0_off;   // number of ranks, offset of this rank's rows in the gathered column
     const double* gpart; // inverse: per-slab shares of the gauge (ngp per member), or nullptr -> scal[1]
     int ngp;
     double* col0;        // forward: compact copy of the Poisson k=0 column, [member * P + row]
@@ -117,6 +126,11 @@ struct YArgs {
     int ngp;
     const double* Ain;  // [ncol]
     const double* Bin;  // [ncol]
+    // y-slab peer mode: mode 1 writes its aggregates straight into every rank's aggr_all[rank]
+    // and rank 0 its gauge into every rank's scal (NVLink peer stores); peer_n = 0 otherwise
+    double* aggr_peer[8];
+    double* scal_peer[8];
+    int peer_n, peer_rank;
 };
 
 struct Handle;
@@ -131,6 +145,9 @@ cudaError_t dist_allgather(Handle* h, const double* send, double* recv, size_t c
 cudaError_t dist_broadcast(Handle* h, double* buf, size_t count, int root);
 cudaError_t dist_allreduce_sum(Handle* h, double* buf, size_t count);
 void dist_destroy(Handle* h);
+cudaError_t dist_barrier(Handle* h);                       // cross-GPU flag barrier on the handle's stream (peer mode)
+int dist_ipc_export(Handle* h, void* out192);
+int dist_ipc_import(Handle* h, const void* all);
 int dist_init(Handle* h, int rank, int nranks, const void* id128);
 int dist_unique_id(void* out128, std::string* err);
 cudaError_t launch_unpack(Handle* h, const double* host_like, double* dev_fields, int slot_of_level0,
@@ -178,6 +195,17 @@ struct Handle {
     double* aggr = nullptr;          // [4][ncol] this rank's carry aggregates
     double* aggr_all = nullptr;      // [dist_n][4][ncol]
     double* carry_in = nullptr;      // [2][ncol]  Ain, Bin
+    // peer-memory exchange (qg_dist_ipc_import): the per-step halo rows, k=0 column, carry aggregates
+    // and gauge are written by the producing kernels straight into the other ranks' memory and
+    // ordered by flag barriers (k_xgpu_barrier) instead of NCCL calls
+    bool peer_ok = false;
+    double* mailbox = nullptr;       // [flags 256][col0_full Pglob][aggr_all n*4*ncol][scal 4]
+    size_t mailbox_doubles = 0;
+    double* peer_q[8] = {};          // every rank's q / psi / mailbox (own pointers at own rank)
+    double* peer_psi[8] = {};
+    double* peer_mail[8] = {};
+    double* own_scal = nullptr;      // the scal array of qg_create (h->scal moves into the mailbox)
+    unsigned long long epoch = 0;    // barrier counter
     double* diag_part = nullptr;     // partial sums for diagnostics
     int diag_blocks = 0;
     int64_t launches = 0;

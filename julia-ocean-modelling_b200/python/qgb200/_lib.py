@@ -58,6 +58,8 @@ SYMBOLS = {
     "qg_launch_count": (C.c_int64, [_P]),
     "qg_nccl_unique_id": (C.c_int, [_P]),
     "qg_dist_init": (C.c_int, [_P, C.c_int, C.c_int, _P]),
+    "qg_dist_ipc_export": (C.c_int, [_P, _P]),
+    "qg_dist_ipc_import": (C.c_int, [_P, _P]),
     "qg_device_layout": (C.c_int, [_P, C.c_int, C.POINTER(_P), C.POINTER(C.c_int64),
                                    C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
 }

@@ -209,6 +209,16 @@ class Session:
         assert len(unique_id) == 128
         self._ck(self._lib.qg_dist_init(self._h, int(rank), int(nranks), C.c_char_p(unique_id)))
 
+    def dist_peer_init(self, allgather):
+        """Switch the per-step exchanges of a y-slab run from NCCL calls to NVLink peer stores
+        (qg_dist_ipc_export / qg_dist_ipc_import).  `allgather(bytes) -> list[bytes]` gathers one
+        192-byte blob per rank in rank order (e.g. torch.distributed.all_gather_object)."""
+        buf = C.create_string_buffer(192)
+        self._ck(self._lib.qg_dist_ipc_export(self._h, buf))
+        blobs = list(allgather(buf.raw))
+        assert all(len(b) == 192 for b in blobs)
+        self._ck(self._lib.qg_dist_ipc_import(self._h, C.c_char_p(b"".join(blobs))))
+
     # -- state transfer -----------------------------------------------------------------
     def upload(self, zeta=None, psi=None, f_store=None):
         for name, a in (("zeta", zeta), ("psi", psi), ("f_store", f_store)):

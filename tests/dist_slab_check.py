@@ -4,7 +4,8 @@
         --master-port 29533 tests/dist_slab_check.py [M P steps]
 
 Every rank builds the same global seeded initial condition, takes its slab of rows, steps it
-through the C ABI in y-slab mode (NCCL halo exchange + carry all-gather), downloads, and compares
+through the C ABI in y-slab mode (exchanges over NVLink peer memory; QG_DIST_NCCL=1: NCCL halo
+exchange + carry all-gather), downloads, and compares
 with the CPU oracle's solution of the GLOBAL problem restricted to the slab (rank 0 prints)."""
 import os
 import sys
@@ -34,12 +35,22 @@ def main():
     dist.broadcast_object_list(ids, src=0)
     ml = slab.local_model(mo, world, cls=qgb200.BaroclinicModel)
     zl, pl, fl = (slab.take_slab(a, rank, world) for a in (zeta, psi, f))
+    def gather_blobs(blob):
+        out = [None] * world
+        dist.all_gather_object(out, blob)
+        return out
+
     with qgb200.Session(ml, device=local) as s:
         s.dist_init(rank, world, ids[0])
+        if not os.environ.get("QG_DIST_NCCL"):
+            s.dist_peer_init(gather_blobs)   # per-step exchanges over NVLink peer memory instead of NCCL
         s.upload(zl, pl, fl)
         s.step(1, steps)
         s.download(zl, pl, fl)
         E, Z = s.diagnostics()
+        if os.environ.get("QG_VERBOSE") and rank == 0:
+            print(f"rank 0: {s.launch_count()} kernel launches", flush=True)
+        dist.barrier()   # nobody frees memory a peer still has mapped
     errs = None
     if rank == 0 or True:
         o.run_steps(mo, zeta, psi, f, o.make_factors(mo, "spectral"), 1, steps)

@@ -237,8 +237,9 @@ def test_error_reporting():
 
 
 def test_y_slab_decomposition_on_two_gpus():
-    """One run split into y-slabs over 2 GPUs (NCCL halo ring + carry all-gather) equals the
-    oracle's global solution; needs two visible GPUs, launched as one process per GPU."""
+    """One run split into y-slabs over 2 GPUs equals the oracle's global solution, with the per-step
+    exchanges done by in-kernel NVLink peer stores + flag barriers and, as a cross-check, by NCCL
+    (QG_DIST_NCCL=1); needs two visible GPUs, launched as one process per GPU."""
     import os
     import subprocess
     import sys
@@ -246,11 +247,14 @@ def test_y_slab_decomposition_on_two_gpus():
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    for M, P in ((256, 256), (512, 1024)):
+    for M, P, nccl in ((256, 256, False), (512, 1024, False), (256, 256, True)):
+        env = dict(os.environ)
+        if nccl:
+            env["QG_DIST_NCCL"] = "1"
         out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
                               "--master-addr", "127.0.0.1", "--master-port", "29541",
                               os.path.join(root, "tests", "dist_slab_check.py"), str(M), str(P), "10"],
-                             capture_output=True, text=True, timeout=600)
+                             capture_output=True, text=True, timeout=600, env=env)
         assert "SLAB_CHECK_OK" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
 
 

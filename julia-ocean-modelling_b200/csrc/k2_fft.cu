@@ -680,7 +680,7 @@ __device__ __forceinline__ double2 w16th(int t) {
 
 template <int LOG2N>
 __global__ void __launch_bounds__(FftLaunch<LOG2N>::THREADS, FftLaunch<LOG2N>::MINB)
-k2_rfft_forward(const FftArgs a, int ngroups_per_member, int ngroups_total) {
+k2_rfft_forward(const FftArgs a, int ngroups_per_member, int ngroups_total, int pf) {
     using L = FftLaunch<LOG2N>;
     using F = RowFft<LOG2N, -1>;
     static_assert(L::RPB == 1, "long-row path: one row per CTA");
@@ -705,7 +705,7 @@ k2_rfft_forward(const FftArgs a, int ngroups_per_member, int ngroups_total) {
             const double2 x1 = __ldg(q1 + lt + t * TPR), x2 = __ldg(q2 + lt + t * TPR);
             v[t] = make_double2(A0 * x1.x + A1 * x2.x, A0 * x1.y + A1 * x2.y);   // (q~[2n], q~[2n+1])
         }
-        {   // next (row, field) of this CTA -> L2
+        if (pf) {   // next (row, field) of this CTA -> L2
             const int gn = grp + gridDim.x;
             if (gn < ngroups_total) {
                 const int mn = gn / ngroups_per_member;
@@ -744,7 +744,7 @@ k2_rfft_forward(const FftArgs a, int ngroups_per_member, int ngroups_total) {
 
 template <int LOG2N>
 __global__ void __launch_bounds__(FftLaunch<LOG2N>::THREADS, FftLaunch<LOG2N>::MINB)
-k4_rfft_inverse(const FftArgs a, int ngroups_per_member, int ngroups_total) {
+k4_rfft_inverse(const FftArgs a, int ngroups_per_member, int ngroups_total, int pf) {
     using L = FftLaunch<LOG2N>;
     using F = RowFft<LOG2N, +1>;
     extern __shared__ __align__(16) double2 fft_smem[];
@@ -771,14 +771,19 @@ k4_rfft_inverse(const FftArgs a, int ngroups_per_member, int ngroups_total) {
         }
         const double2* __restrict__ in =
             reinterpret_cast<const double2*>(a.S + member * a.sstride + (int64_t)row * a.pl.ncol);
-        double2 v[8];
+        // Pre-processing by Hermitian pairs: the points k and N-k need the same four spectral values,
+        // so a thread forms both V[k] = E + iO and V[N-k] = conj(E) + i conj(O) from one set of loads
+        // (half the L2 traffic of loading per point) and stages them in shared memory for pass 0.
 #pragma unroll
-        for (int t = 0; t < 8; ++t) {
-            const int k = lt + t * TPR;   // 0 .. N-1
+        for (int t = 0; t < 4; ++t) {
+            const int k = lt + t * TPR;   // 0 .. N/2-1
             if (k == 0) {
                 const double2 s0 = __ldg(in), sN = __ldg(in + N);   // (U1[0], U2[0]), (U1[N], U2[N])
                 const double X0 = P0 * (s0.x - gauge) + P1 * s0.y, XN = P0 * sN.x + P1 * sN.y;
-                v[t] = make_double2(X0 + XN, X0 - XN);
+                s[swz(0)] = make_double2(X0 + XN, X0 - XN);
+                // the self-paired point N/2: V = 2 conj(X[N/2])
+                const double2 h1 = __ldg(in + N / 2), h2 = __ldg(in + M - N / 2);
+                s[swz(N / 2)] = make_double2(2.0 * (P0 * h1.x + P1 * h2.x), -2.0 * (P0 * h1.y + P1 * h2.y));
             } else {
                 // X[k] = P0 U1[k] + P1 U2[k];  U1[k] = slot k, U2[k] = slot M-k
                 const double2 a1 = __ldg(in + k), a2 = __ldg(in + M - k);
@@ -788,7 +793,21 @@ k4_rfft_inverse(const FftArgs a, int ngroups_per_member, int ngroups_total) {
                 const double2 E = make_double2(Xk.x + Xm.x, Xk.y - Xm.y);                        // X[k] + conj X[N-k]
                 const double2 D = make_double2(Xk.x - Xm.x, Xk.y + Xm.y);                        // X[k] - conj X[N-k]
                 const double2 O = cmul(cmul(w0c, cconj(w16th(t))), D);                           // W^-k (..)
-                v[t] = make_double2(E.x - O.y, E.y + O.x);                                       // E + i O
+                s[swz(k)] = make_double2(E.x - O.y, E.y + O.x);                                  // E + i O
+                s[swz(N - k)] = make_double2(E.x + O.y, O.x - E.y);                              // conj(E) + i conj(O)
+            }
+        }
+        __syncthreads();
+        double2 v[8];
+#pragma unroll
+        for (int t = 0; t < 8; ++t) v[t] = s[swz(lt + t * TPR)];
+        __syncthreads();   // pass 0 overwrites the buffer
+        if (pf) {   // next (row, layer) of this CTA -> L2: a single resident CTA cannot hide the DRAM round trip
+            const int gn = grp + gridDim.x;
+            if (gn < ngroups_total) {
+                const int mn = gn / ngroups_per_member;
+                const int rn = (gn - mn * ngroups_per_member) >> 1;
+                prefetch_row_l2(a.S + mn * a.sstride + (int64_t)rn * a.pl.ncol, M * 16, lt, TPR);
             }
         }
         fft.template run<false>(v, s, lt);
@@ -1003,7 +1022,8 @@ static cudaError_t launch_long(Handle* h, const FftArgs& a) {
     const int total = gpm * h->nm;
     int grid = num_sms() * blocks_per_sm;
     if (grid > total) grid = total;
-    kern<<<grid, L::THREADS, L::SMEM, h->stream>>>(a, gpm, total);
+    static const int pf = getenv("QG_FFT_PF") ? atoi(getenv("QG_FFT_PF")) : 1;
+    kern<<<grid, L::THREADS, L::SMEM, h->stream>>>(a, gpm, total, pf);
     return cudaGetLastError();
 }
 

@@ -327,6 +327,15 @@ def main():
     if not (np.all(np.isfinite(E)) and np.all(np.isfinite(Z))):
         raise SystemExit("bench.py: state went non-finite during the timed region")
 
+    # ---- the same K steps without the per-launch events (CUDA-graph replay), informational -------
+    barrier()
+    g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    g0.record(stream)
+    sess.step(W + K + 1, K)
+    g1.record(stream)
+    barrier()
+    ms_graph = g0.elapsed_time(g1)
+
     # ---- end-to-end timing through host buffers ("e2e") -------------------------------------
     views[2][...] = 0.0
     zeta0, psi0 = initial_state()
@@ -344,10 +353,10 @@ def main():
     h2d = 2 * (n_elem // 3) * 8
     d2h = 2 * n_elem * 8
 
-    tmax = torch.tensor([ms_total, e2e_s * 1e3], dtype=torch.float64, device="cuda")
+    tmax = torch.tensor([ms_total, e2e_s * 1e3, ms_graph], dtype=torch.float64, device="cuda")
     if dist is not None:
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
-    ms_total, e2e_ms = float(tmax[0]), float(tmax[1])
+    ms_total, e2e_ms, ms_graph = float(tmax[0]), float(tmax[1]), float(tmax[2])
     sess.close()
 
     if rank == 0:
@@ -364,7 +373,8 @@ def main():
         small = {k: round(per[k] * 1e6, 2) for k in per if k not in KERNEL_BYTES and per[k]}
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
-            "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "ms_per_step": ms_total / K, "ms_per_step_graph_replay": ms_graph / K,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
             "config": {"workload": f"Phillips two-layer {M}x{P}, Float64, "
                                    + (f"ensemble of {world * mb} members, {mb} batched per B200 (BASELINE.json config 5 "

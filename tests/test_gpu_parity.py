@@ -61,6 +61,8 @@ def test_ten_steps_against_golden(name, golden_dir):
     # persistent y-solve with a ragged last CTA: 33 chunks over 4 CTAs of 9 (two 144-row TMA boxes
     # per tile), 65 chunks over 8 CTAs of 9 (the last CTA owns 2 chunks), and radix-16 rows (M = 256)
     (256, 1056, "spectral"), (64, 2080, "spectral"), (256, 256, "direct"),
+    # one chunk per column (the smoke-test shape) and 17 chunks over 2 CTAs of 9
+    (64, 32, "direct"), (128, 544, "spectral"),
 ])
 def test_ten_steps_against_oracle(M, P, backend):
     """psi, q (and the RHS history) after 10 steps; covers power-of-two and general M,

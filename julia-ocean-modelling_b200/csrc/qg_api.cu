@@ -421,10 +421,13 @@ static int do_evolve_psi(Handle* h) {
 }
 
 static int do_evolve_zeta(Handle* h, int timestep) {
+    // peer mode: K1 stores its edge rows into the neighbours' ghost rows; they are read by the next
+    // step's K1 only, after the barriers of evolve_psi (two evolve_zeta calls in a row - not a
+    // reference pattern - get a barrier of their own)
+    if (h->peer_ok && h->q_halo_pending) QG_CUDA(h, dist_barrier(h));
     QG_CUDA(h, launch_zeta(h, timestep));
-    // peer mode: K1 stored its edge rows into the neighbours' ghost rows; they are read by the next
-    // step's K1 only, after the barriers of evolve_psi
     if (h->dist_n > 1 && !h->peer_ok) QG_CUDA(h, dist_halo_exchange(h, h->q, h->qcur));
+    h->q_halo_pending = h->peer_ok;
     return QG_OK;
 }
 

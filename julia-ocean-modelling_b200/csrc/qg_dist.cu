@@ -153,6 +153,7 @@ cudaError_t dist_barrier(Handle* h) {
     for (int r = 0; r < h->dist_n; ++r) p.f[r] = reinterpret_cast<unsigned long long*>(h->peer_mail[r]);
     ++h->epoch;
     h->launches++;
+    h->q_halo_pending = false;
     k_xgpu_barrier<<<1, 32, 0, h->stream>>>(p, h->dist_rank, h->dist_n, h->epoch);
     return cudaGetLastError();
 }

@@ -206,6 +206,7 @@ struct Handle {
     double* peer_mail[8] = {};
     double* own_scal = nullptr;      // the scal array of qg_create (h->scal moves into the mailbox)
     unsigned long long epoch = 0;    // barrier counter
+    bool q_halo_pending = false;     // K1 has pushed q rows to the neighbours and no barrier has run since
     double* diag_part = nullptr;     // partial sums for diagnostics
     int diag_blocks = 0;
     int64_t launches = 0;

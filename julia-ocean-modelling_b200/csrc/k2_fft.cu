@@ -1105,7 +1105,7 @@ cudaError_t launch_fft_inverse(Handle* h, double* psi_fields, int use_gauge) {
         a.pimg_lo = h->peer_psi[(h->dist_rank + h->dist_n - 1) % h->dist_n] + off;
         a.pimg_hi = h->peer_psi[(h->dist_rank + 1) % h->dist_n] + off;
     }
-    if (h->plan.ts_ok && h->dist_n == 1) {   // K3 left per-slab shares of the gauge instead of running k3_gauge
+    if (h->gauge_parts) {   // K3 left per-slab shares of the gauge instead of running k3_gauge
         a.gpart = h->gpart;
         a.ngp = h->plan.ngp;
     }

@@ -695,7 +695,9 @@ __device__ __forceinline__ double k0_column_total(const YArgs& a, int member, do
 #define K3_ACC(i) do { } while (0)
 #endif
 
-template <int MODE>   // 0: cyclic over the local rows; 1 / 2: y-slab mode, see YArgs::mode
+// CSW = lanes of the CTA-level closure = largest cluster size served: 8 (portable) or 16 (non-portable
+// clusters, 512 rows x 16 CTAs = 8192 rows in one pass)
+template <int MODE, int CSW>   // MODE 0: cyclic over the local rows; 1 / 2: y-slab mode, see YArgs::mode
 __global__ void __launch_bounds__(TP_THREADS, 2)
 k3_ysolve_pipe(const __grid_constant__ CUtensorMap tmS, const __grid_constant__ CUtensorMap tmT, const YArgs a,
                int nchunk, int boxrows, int nslab, int nwork) {
@@ -716,8 +718,8 @@ k3_ysolve_pipe(const __grid_constant__ CUtensorMap tmS, const __grid_constant__ 
     double* ctab = tile + (size_t)nchunk * 32 * TS_WC;                 // [2 parities][CT_ROWS][16]
     double* sF = ctab + 2 * CT_ROWS * TS_WC;                           // [nchunk][TS_LD]
     double* sG = sF + nchunk * TS_LD;
-    double* sEx = sG + nchunk * TS_LD;                                 // [2 parities][8 CTAs][16 cols][FF,RR,X,Y]
-    uint64_t* bar = reinterpret_cast<uint64_t*>(sEx + 2 * 8 * TS_WC * 4);   // [0] tile, [1..2] exchange parity
+    double* sEx = sG + nchunk * TS_LD;                                 // [2 parities][CSW CTAs][16 cols][FF,RR,X,Y]
+    uint64_t* bar = reinterpret_cast<uint64_t*>(sEx + 2 * CSW * TS_WC * 4);   // [0] tile, [1..2] exchange parity
 
     const int c0 = cr * nchunk;                     // first global chunk of this CTA
     const int nact = max(0, min(nchunk, C - c0));   // chunks that hold rows (all of them full: P % 32 == 0)
@@ -749,7 +751,8 @@ k3_ysolve_pipe(const __grid_constant__ CUtensorMap tmS, const __grid_constant__ 
     // they fall to clusters that would otherwise finish one slab early; the slab pass itself
     // leaves column 0 alone
     __shared__ double red_sh[32];
-    const int nmember = MODE == 0 ? nwork / nslab : 0;   // y-slab mode: k3_pre solves the gathered column
+    const bool k0ext = MODE != 0 || a.k0_external;         // k3_pre has solved the k = 0 column (y-slab mode, P > 4096)
+    const int nmember = k0ext ? 0 : nwork / nslab;
     int tot_member = -1;
     double pinscale = 0.0;
 
@@ -767,10 +770,10 @@ k3_ysolve_pipe(const __grid_constant__ CUtensorMap tmS, const __grid_constant__ 
         const int col = col0 + l;
         const int par = it & 1;
         const double* ct = ctab + (size_t)par * CT_ROWS * TS_WC;
-        double* ex = sEx + (size_t)par * 8 * TS_WC * 4;
+        double* ex = sEx + (size_t)par * CSW * TS_WC * 4;
         uint64_t* xbar = &bar[1 + par];
         if (a.pinned && c0 == 0 && a.row0 == 0 && member != tot_member) {   // block-uniform: this CTA owns row 0
-            pinscale = MODE == 0 ? k0_column_total(a, member, red_sh) : a.scal[member * 4 + 0];
+            pinscale = k0ext ? a.scal[member * 4 + 0] : k0_column_total(a, member, red_sh);
             tot_member = member;
         }
         if (tid == 0) mbar_expect_tx(xbar, (uint32_t)CS * TS_WC * 4 * sizeof(double));
@@ -870,7 +873,7 @@ k3_ysolve_pipe(const __grid_constant__ CUtensorMap tmS, const __grid_constant__ 
             K3_ACC(5);
             // CTA-level closure, again as a parallel cyclic reduction: lane i (mod 8) of the half-warp
             // holds CTA i's aggregate and the affine maps compose by shuffles
-            const int i8 = slot & 7;
+            const int i8 = slot & (CSW - 1);
             double FFl = 0.0, RRl = 1.0, Xl = 0.0, Yl = 0.0;
             if (i8 < CS) {
                 const double2 q0 = *reinterpret_cast<const double2*>(ex + ((size_t)i8 * TS_WC + cl) * 4);
@@ -879,26 +882,26 @@ k3_ysolve_pipe(const __grid_constant__ CUtensorMap tmS, const __grid_constant__ 
             }
             double R1 = RRl, T1 = FFl;   // inclusive forward composition over CTAs 0..i
 #pragma unroll
-            for (int d = 1; d < 8; d <<= 1) {
-                const double Rp = __shfl_up_sync(0xffffffffu, R1, d, 8);
-                const double Tp = __shfl_up_sync(0xffffffffu, T1, d, 8);
+            for (int d = 1; d < CSW; d <<= 1) {
+                const double Rp = __shfl_up_sync(0xffffffffu, R1, d, CSW);
+                const double Tp = __shfl_up_sync(0xffffffffu, T1, d, CSW);
                 if (i8 >= d) {
                     T1 = fma(R1, Tp, T1);
                     R1 *= Rp;
                 }
             }
-            double Rx = __shfl_up_sync(0xffffffffu, R1, 1, 8), Tx = __shfl_up_sync(0xffffffffu, T1, 1, 8);
+            double Rx = __shfl_up_sync(0xffffffffu, R1, 1, CSW), Tx = __shfl_up_sync(0xffffffffu, T1, 1, CSW);
             if (i8 == 0) { Rx = 1.0; Tx = 0.0; }
             if (MODE == 1) {
                 // y-slab mode, first kernel: fold the cluster's CTAs into one rank-level aggregate
                 // (same affine composition one level up) and stop; the ranks exchange these.
                 double Xr = Rx * fma(Yl, Tx, Xl), Yr = Rx * (Yl * Rx);
 #pragma unroll
-                for (int d = 4; d > 0; d >>= 1) {
-                    Xr += __shfl_xor_sync(0xffffffffu, Xr, d, 8);
-                    Yr += __shfl_xor_sync(0xffffffffu, Yr, d, 8);
+                for (int d = CSW / 2; d > 0; d >>= 1) {
+                    Xr += __shfl_xor_sync(0xffffffffu, Xr, d, CSW);
+                    Yr += __shfl_xor_sync(0xffffffffu, Yr, d, CSW);
                 }
-                const double Tt = __shfl_sync(0xffffffffu, T1, 7, 8), Rt = __shfl_sync(0xffffffffu, R1, 7, 8);
+                const double Tt = __shfl_sync(0xffffffffu, T1, CSW - 1, CSW), Rt = __shfl_sync(0xffffffffu, R1, CSW - 1, CSW);
                 if (cr == 0 && slot == 0 && col0 + cl < ncol) {
                     a.aggr[0 * ncol + col0 + cl] = Tt;
                     a.aggr[1 * ncol + col0 + cl] = Rt;
@@ -916,27 +919,27 @@ k3_ysolve_pipe(const __grid_constant__ CUtensorMap tmS, const __grid_constant__ 
                 continue;   // warp-uniform; sF / sG are rewritten only after the next iteration's barrier
             }
             // carry into CTA 0: cyclic closure (y at the last row), or handed in by the rank below
-            const double as0 = MODE == 2 ? asIn : __shfl_sync(0xffffffffu, T1, 7, 8) * inv1;
+            const double as0 = MODE == 2 ? asIn : __shfl_sync(0xffffffffu, T1, CSW - 1, CSW) * inv1;
             const double as_i = fma(Rx, as0, Tx);          // forward carry into CTA i
             const double GGp = fma(Yl, as_i, Xl);          // CTA i's backward aggregate with its true carry
             double R2 = RRl, T2 = GGp;   // inclusive backward composition over CTAs 7..i
 #pragma unroll
-            for (int d = 1; d < 8; d <<= 1) {
-                const double Rp = __shfl_down_sync(0xffffffffu, R2, d, 8);
-                const double Tp = __shfl_down_sync(0xffffffffu, T2, d, 8);
-                if (i8 + d < 8) {
+            for (int d = 1; d < CSW; d <<= 1) {
+                const double Rp = __shfl_down_sync(0xffffffffu, R2, d, CSW);
+                const double Tp = __shfl_down_sync(0xffffffffu, T2, d, CSW);
+                if (i8 + d < CSW) {
                     T2 = fma(R2, Tp, T2);
                     R2 *= Rp;
                 }
             }
             // carry into the last CTA: cyclic closure (z at row 0), or handed in by the rank above
-            const double blast = MODE == 2 ? beIn : __shfl_sync(0xffffffffu, T2, 0, 8) * inv1;
-            Rx = __shfl_down_sync(0xffffffffu, R2, 1, 8);
-            Tx = __shfl_down_sync(0xffffffffu, T2, 1, 8);
-            if (i8 == 7) { Rx = 1.0; Tx = 0.0; }
+            const double blast = MODE == 2 ? beIn : __shfl_sync(0xffffffffu, T2, 0, CSW) * inv1;
+            Rx = __shfl_down_sync(0xffffffffu, R2, 1, CSW);
+            Tx = __shfl_down_sync(0xffffffffu, T2, 1, CSW);
+            if (i8 == CSW - 1) { Rx = 1.0; Tx = 0.0; }
             const double be_i = fma(Rx, blast, Tx);        // backward carry into CTA i
-            const double a_s = __shfl_sync(0xffffffffu, as_i, cr, 8);
-            const double b_e = __shfl_sync(0xffffffffu, be_i, cr, 8);
+            const double a_s = __shfl_sync(0xffffffffu, as_i, cr, CSW);
+            const double b_e = __shfl_sync(0xffffffffu, be_i, cr, CSW);
             const double A = fma(Rpre, a_s, pF);
             const double Gp = fma(A, hh, G);
             // inclusive backward (suffix) scan of x -> rho x + G'
@@ -967,14 +970,14 @@ k3_ysolve_pipe(const __grid_constant__ CUtensorMap tmS, const __grid_constant__ 
             const double kap = ct[CT_KAP * TS_WC + l];
             const bool cvalid = col < ncol;
             // column 0 (k = 0 Poisson): written by k0_column_solve (mode 0) / taken from k3_pre's solution (mode 2)
-            const bool wr = col < ncol && (MODE != 0 || col != 0);
+            const bool wr = col < ncol && (k0ext || col != 0);
             const double* __restrict__ k0 = a.k0sol + (int64_t)member * a.preP + a.row0 + j0;
             double* out = a.S + member * a.sstride + (int64_t)j0 * ncol + (cvalid ? col : 0);
             double u0 = 0.0;
 #pragma unroll
             for (int i = 0; i < 32; ++i) {
                 double u = kap * fma(A, ct[(CT_CA + i) * TS_WC + l], fma(B, ct[(CT_CB + i) * TS_WC + l], v[i]));
-                if (MODE != 0 && col == 0) u = k0[i];
+                if (k0ext && col == 0) u = k0[i];
                 if (wr) *out = u;
                 out += ncol;
                 if (i == 0) u0 = u;   // kap = 0 for the singular column: its gauge share is its solved value 0
@@ -1074,32 +1077,41 @@ static cudaError_t launch_tma_kernel(Handle* h, const YArgs& a) {
         KernelTimer t(h, QG_K_YSOLVE);
         return cudaLaunchKernelEx(&cfg, kern, h->tm_S, a, pl.ts_nchunk);
     }
-    // single-GPU mode: persistent clusters, one wave
-    static size_t configured_p = 0;
+    // persistent clusters, one wave; clusters of up to 8 CTAs are portable, 16 (P > 4096) opt in
+    const bool wide = pl.tp_CS > 8;
+    const int csw = wide ? 16 : 8;
+    static size_t configured_p[2] = {0, 0};
+    attr[0].val.clusterDim.x = pl.tp_CS;
     cfg.blockDim = dim3(TP_THREADS, 1, 1);
-    cfg.dynamicSmemBytes = ((size_t)pl.ts_nchunk * 32 * TS_WC + 2 * CT_ROWS * TS_WC + 2 * pl.ts_nchunk * TS_LD +
-                            2 * 8 * TS_WC * 4) * sizeof(double) + 32;
-    if (cfg.dynamicSmemBytes > configured_p) {
-        for (auto k : {k3_ysolve_pipe<0>, k3_ysolve_pipe<1>, k3_ysolve_pipe<2>}) {
+    cfg.dynamicSmemBytes = ((size_t)pl.tp_nchunk * 32 * TS_WC + 2 * CT_ROWS * TS_WC + 2 * pl.tp_nchunk * TS_LD +
+                            2 * csw * TS_WC * 4) * sizeof(double) + 32;
+    auto pkern = wide ? (a.mode == 1 ? k3_ysolve_pipe<1, 16> : (a.mode == 2 ? k3_ysolve_pipe<2, 16> : k3_ysolve_pipe<0, 16>))
+                      : (a.mode == 1 ? k3_ysolve_pipe<1, 8> : (a.mode == 2 ? k3_ysolve_pipe<2, 8> : k3_ysolve_pipe<0, 8>));
+    if (cfg.dynamicSmemBytes > configured_p[wide]) {
+        auto set = [&](auto k) {
             cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cfg.dynamicSmemBytes);
-            if (e != cudaSuccess) return e;
-        }
-        configured_p = cfg.dynamicSmemBytes;
+            if (e == cudaSuccess && wide) e = cudaFuncSetAttribute(k, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+            return e;
+        };
+        cudaError_t e = wide ? set(k3_ysolve_pipe<0, 16>) : set(k3_ysolve_pipe<0, 8>);
+        if (e == cudaSuccess) e = wide ? set(k3_ysolve_pipe<1, 16>) : set(k3_ysolve_pipe<1, 8>);
+        if (e == cudaSuccess) e = wide ? set(k3_ysolve_pipe<2, 16>) : set(k3_ysolve_pipe<2, 8>);
+        if (e != cudaSuccess) return e;
+        configured_p[wide] = cfg.dynamicSmemBytes;
     }
-    auto pkern = a.mode == 1 ? k3_ysolve_pipe<1> : (a.mode == 2 ? k3_ysolve_pipe<2> : k3_ysolve_pipe<0>);
     if (h->plan.tp_ncl == 0) {   // clusters the device holds at once
         int ncl = 0;
-        cfg.gridDim = dim3(nslab * pl.ts_CS * h->nm, 1, 1);
-        if (cudaOccupancyMaxActiveClusters(&ncl, k3_ysolve_pipe<0>, &cfg) == cudaSuccess && ncl > 0) h->plan.tp_ncl = ncl;
-        else { h->plan.tp_ncl = 2 * 148 / pl.ts_CS; (void)cudaGetLastError(); }
+        cfg.gridDim = dim3(nslab * pl.tp_CS * h->nm, 1, 1);
+        if (cudaOccupancyMaxActiveClusters(&ncl, pkern, &cfg) == cudaSuccess && ncl > 0) h->plan.tp_ncl = ncl;
+        else { h->plan.tp_ncl = 2 * 148 / pl.tp_CS; (void)cudaGetLastError(); }
         if (ncl_env > 0) h->plan.tp_ncl = ncl_env;
-        if (getenv("QG_VERBOSE")) fprintf(stderr, "qgb200: y-solve persistent clusters: %d x %d CTAs\n", h->plan.tp_ncl, pl.ts_CS);
+        if (getenv("QG_VERBOSE")) fprintf(stderr, "qgb200: y-solve persistent clusters: %d x %d CTAs\n", h->plan.tp_ncl, pl.tp_CS);
     }
     const int nwork = nslab * h->nm;
     // work items = slabs + one k=0 column per member; small grids get clusters of their own for the latter
     const int nitems = nwork + (a.mode == 0 ? h->nm : 0);
     const int ncl = h->plan.tp_ncl < nitems ? h->plan.tp_ncl : nitems;
-    cfg.gridDim = dim3(ncl * pl.ts_CS, 1, 1);
+    cfg.gridDim = dim3(ncl * pl.tp_CS, 1, 1);
 #ifdef QG_K3_TRACE
     static long long* dbuf = nullptr;
     static int calls = 0;
@@ -1111,7 +1123,7 @@ static cudaError_t launch_tma_kernel(Handle* h, const YArgs& a) {
     cudaError_t te;
     {
         KernelTimer t(h, QG_K_YSOLVE);
-        te = cudaLaunchKernelEx(&cfg, pkern, h->tm_S2, h->tm_T, a, pl.ts_nchunk, pl.tp_boxrows, nslab, nwork);
+        te = cudaLaunchKernelEx(&cfg, pkern, h->tm_S2, h->tm_T, a, pl.tp_nchunk, pl.tp_boxrows, nslab, nwork);
     }
     if (++calls == 20) {
         cudaStreamSynchronize(h->stream);
@@ -1131,13 +1143,14 @@ static cudaError_t launch_tma_kernel(Handle* h, const YArgs& a) {
     return te;
 #else
     KernelTimer t(h, QG_K_YSOLVE);
-    return cudaLaunchKernelEx(&cfg, pkern, h->tm_S2, h->tm_T, a, pl.ts_nchunk, pl.tp_boxrows, nslab, nwork);
+    return cudaLaunchKernelEx(&cfg, pkern, h->tm_S2, h->tm_T, a, pl.tp_nchunk, pl.tp_boxrows, nslab, nwork);
 #endif
 }
 
 // y-slab mode: gather the k=0 column, solve it redundantly on every rank, sweep + exchange the
 // rank-level carry aggregates, close the recurrences over the ranks, apply.
 static cudaError_t launch_ysolve_dist(Handle* h, int pinned) {
+    h->gauge_parts = false;   // rank 0 evaluates the gauge (k3_gauge) and hands it to the others
     YArgs a{};
     a.pl = h->plan;
     a.S = h->S;
@@ -1201,19 +1214,23 @@ cudaError_t launch_ysolve(Handle* h, int pinned, int /*unused*/) {
     a.pinned = pinned;
     a.col0 = h->col0;
     a.preP = h->plan.P;
-    if (h->plan.ts_ok) {   // the gauge is assembled from per-slab partial sums (no extra kernel)
+    static const bool force_v1 = env_int("QG_K3_V1", 0) != 0;
+    const bool pipe = h->plan.tp_ok && !force_v1;          // persistent kernel
+    const bool tma = pipe || h->plan.ts_ok;                // either TMA-staged kernel
+    h->gauge_parts = tma;
+    if (tma) {   // the gauge is assembled from per-slab partial sums (no extra kernel)
         a.gpart = h->gpart;
         a.ngp = h->plan.ngp;
     }
-    static const bool force_v1 = env_int("QG_K3_V1", 0) != 0;
-    const bool pipe = h->plan.ts_ok && h->plan.tp_ok && !force_v1;   // k3_ysolve_pipe solves the k=0 column itself
-    if (!pipe) {
+    // the persistent kernel solves the k = 0 column itself up to 4096 rows (16 per thread of one CTA)
+    a.k0_external = (pipe && h->plan.P > 16 * TP_THREADS) ? 1 : 0;
+    if (!pipe || a.k0_external) {
         KernelTimer t(h, QG_K_YPRE);
         launch_pre(a, h->nm, h->stream);
     }
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
-    if (h->plan.ts_ok) {
+    if (tma) {
         e = launch_tma_kernel(h, a);
     } else {
         const Plan& pl = h->plan;
@@ -1244,7 +1261,7 @@ cudaError_t launch_ysolve(Handle* h, int pinned, int /*unused*/) {
         }
     }
     if (e != cudaSuccess) return e;
-    if (!h->plan.ts_ok) {
+    if (!tma) {
         KernelTimer t(h, QG_K_GAUGE);
         k3_gauge<<<h->nm, 256, 0, h->stream>>>(a);
     }

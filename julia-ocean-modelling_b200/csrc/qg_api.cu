@@ -285,8 +285,14 @@ cudaError_t build_plan(Handle* h) {
     // (or two equal ones) per CTA tile, and all per-column constants in one table so that they
     // arrive with the tile:  rows 0-31 cA[i] = r^(i+1) * sum_{m<32-i} r^(2m), rows 32-63
     // cB[i] = r^(32-i), then r, kap, r^32, h32, 1/(1-r^P), pin weight, gauge weight, spare.
-    pl.tp_ok = (pl.ts_ok && P % 32 == 0) ? 1 : 0;
-    pl.tp_boxrows = pl.ts_nchunk * 32 <= 256 ? pl.ts_nchunk * 32 : pl.ts_nchunk * 16;
+    {
+        int cs = 1;
+        while (cs < 16 && (pl.C + cs - 1) / cs > 16) cs *= 2;
+        pl.tp_CS = cs;
+        pl.tp_nchunk = (pl.C + cs - 1) / cs;
+    }
+    pl.tp_ok = (pl.tp_nchunk <= 16 && (pl.ncol % 16) == 0 && P % 32 == 0) ? 1 : 0;
+    pl.tp_boxrows = pl.tp_nchunk * 32 <= 256 ? pl.tp_nchunk * 32 : pl.tp_nchunk * 16;
     if (pl.tp_ok) {
         const int NR = 72;
         std::vector<double> ct((size_t)NR * pl.ncol, 0.0);
@@ -522,7 +528,7 @@ int qg_create(const qg_params* p, int device, int nmembers, void* stream, qg_han
     }
     rc = make_tensor_map(h, &h->tm_q, h->q, K1_TX + 2 * GHOST, h->k1_ty + 2);
     if (rc == QG_OK) rc = make_tensor_map(h, &h->tm_psi, h->psi, K1_TX + 2 * GHOST, h->k1_ty + 2 * GHOST);
-    if (rc == QG_OK && h->plan.ts_ok) rc = make_tensor_map_S(h);
+    if (rc == QG_OK && (h->plan.ts_ok || h->plan.tp_ok)) rc = make_tensor_map_S(h);
     if (rc != QG_OK) return bail(rc);
     QG_TRY(cudaStreamSynchronize(h->stream));
 #undef QG_TRY
@@ -905,8 +911,8 @@ int qg_dist_init(qg_handle* h, int rank, int nranks, const void* unique_id128) {
     if (nranks < 2 || nranks > 8 || rank < 0 || rank >= nranks)
         return fail(h, QG_ERR_INVALID, "qg_dist_init: need 2 <= nranks <= 8 and 0 <= rank < nranks");
     if (h->nm != 1) return fail(h, QG_ERR_INVALID, "qg_dist_init: y-slab mode takes one member per handle");
-    if (h->g.P % 32 != 0 || !h->plan.ts_ok)
-        return fail(h, QG_ERR_INVALID, "qg_dist_init: local row count must be a multiple of 32 and at most 4096");
+    if (h->g.P % 32 != 0 || !h->plan.tp_ok)
+        return fail(h, QG_ERR_INVALID, "qg_dist_init: local row count must be a multiple of 32 and at most 8192");
     if ((int64_t)h->g.P * nranks > 16384) return fail(h, QG_ERR_INVALID, "qg_dist_init: global P > 16384");
     QG_CUDA(h, cudaSetDevice(h->device));
     int rc = dist_init(h, rank, nranks, unique_id128);
@@ -914,7 +920,7 @@ int qg_dist_init(qg_handle* h, int rank, int nranks, const void* unique_id128) {
     // the cyclic closure now spans the global row count: rebuild the coefficient tables
     free_plan(h);
     QG_CUDA(h, build_plan(h));
-    if (h->plan.ts_ok && (rc = make_tensor_map_S(h))) return rc;   // the column table moved with the plan
+    if ((h->plan.ts_ok || h->plan.tp_ok) && (rc = make_tensor_map_S(h))) return rc;   // the column table moved with the plan
     h->have_state = false;
     return QG_OK;
 }

@@ -74,7 +74,8 @@ struct Plan {
     int wpc, CS, m;          // warps per CTA, cluster size, chunks per warp (register variant)
     int ts_ok, ts_CS, ts_nchunk;   // TMA-staged variant: usable, cluster size, chunks per CTA
     int tp_ncl;              // persistent variant: clusters resident at once (0 = not queried yet)
-    int tp_ok, tp_boxrows;   // persistent variant usable (P % 32 == 0); rows per TMA box (<= 256)
+    int tp_ok, tp_boxrows;   // persistent variant usable (P % 32 == 0, <= 8192 rows); rows per TMA box (<= 256)
+    int tp_CS, tp_nchunk;    // its cluster size (<= 16, non-portable above 8) and chunks per CTA
     double* coltab;          // [72][ncol] per-column constants of the persistent y-solve (k3_ysolve.cu)
     double2* tw;             // exp(-2 pi i n / M), n < M
     double *rtab, *kap, *rho32, *h32, *rhoL, *hL, *inv1mrP, *pinw, *gw;   // per real column
@@ -123,6 +124,7 @@ struct YArgs {
     int mode;
     double* aggr;       // [4][ncol]
     double* gpart;      // [member][ngp] per-slab shares of psi~1(0,0); nullptr: k3_gauge -> scal[1]
+    int k0_external;    // persistent kernel: k3_pre has solved the k = 0 column (P > 4096), do not redo it
     int ngp;
     const double* Ain;  // [ncol]
     const double* Bin;  // [ncol]
@@ -186,6 +188,7 @@ struct Handle {
     bool snap_pending = false;
     double* col0 = nullptr;          // [nm][P] compact Poisson k=0 column (written by K2)
     double* gpart = nullptr;         // [nm][ngp] gauge partial sums (written by K3, summed by K4)
+    bool gauge_parts = false;        // the last y-solve left gpart (else scal[1] holds the gauge)
     // ---- y-slab decomposition of one run over several GPUs (qg_dist_init) ----
     int dist_n = 1, dist_rank = 0;
     int Pglob = 0;                   // global row count (= P when not distributed)

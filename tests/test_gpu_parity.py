@@ -63,6 +63,8 @@ def test_ten_steps_against_golden(name, golden_dir):
     (256, 1056, "spectral"), (64, 2080, "spectral"), (256, 256, "direct"),
     # one chunk per column (the smoke-test shape) and 17 chunks over 2 CTAs of 9
     (64, 32, "direct"), (128, 544, "spectral"),
+    # more than 4096 rows: clusters of 16 CTAs (non-portable size), k = 0 column from k3_pre
+    (64, 8192, "spectral"), (128, 6144, "spectral"),
 ])
 def test_ten_steps_against_oracle(M, P, backend):
     """psi, q (and the RHS history) after 10 steps; covers power-of-two and general M,

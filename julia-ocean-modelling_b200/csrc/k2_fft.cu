@@ -93,38 +93,45 @@ __device__ __forceinline__ void bfly8(double2 (&a)[8]) {
 }
 
 // Per-thread FFT engine for rows of N = 2^LOG2N points, 8 points per thread.
-template <int LOG2N, int SIGN>
+// W8S: keep the per-pass base twiddles in shared memory instead of registers (the 1024-thread
+// long-row kernels have 64 registers per thread and spilled with them resident)
+template <int LOG2N, int SIGN, bool W8S = false>
 struct RowFft {
     static constexpr int N = 1 << LOG2N;
     static constexpr int TPR = N / 8;
     static constexpr int NB8 = LOG2N / 3;
     static constexpr int REM = LOG2N % 3;
     static constexpr int NW8 = NB8 > 1 ? NB8 - 1 : 1;
-    double2 w8[NW8];   // base twiddle of radix-8 pass p = 1 .. NB8-1
-    double2 wr[4];     // base twiddles of the remainder pass (2 butterflies radix-4, 4 radix-2)
+    double2 w8[W8S ? 1 : NW8];   // base twiddle of radix-8 pass p = 1 .. NB8-1 (registers)
+    double2* w8s;                // ... or [NW8][blockDim.x] in shared memory, this thread's column
+    double2 wr0;       // base twiddle of the remainder pass for butterfly 0 (index lt); butterfly b sits
+                       // TPR = N/8 further on, i.e. its twiddle is wr0 turned by b eighths of a half turn
+    // wr0 * exp(SIGN * i * pi * b / 4)
+    __device__ __forceinline__ double2 wrem(int b) const {
+        const double h = 0.70710678118654752440;
+        switch (b & 3) {
+            case 0: return wr0;
+            case 1: return cmul(wr0, make_double2(h, SIGN * h));
+            case 2: return muli<SIGN>(wr0);
+            default: return cmul(wr0, make_double2(-h, SIGN * h));
+        }
+    }
 
     // `stride`: the table holds exp(-2 pi i n / (stride * N))
-    __device__ __forceinline__ void init(const double2* __restrict__ tw, int lt, int stride = 1) {
+    __device__ __forceinline__ void init(const double2* __restrict__ tw, int lt, int stride = 1,
+                                         double2* w8_smem = nullptr) {
         int Ns = 8;
+        w8s = w8_smem + threadIdx.x;
 #pragma unroll
         for (int p = 1; p < NB8; ++p) {
             const int k = lt & (Ns - 1);
-            w8[p - 1] = twid<SIGN>(tw, stride * (k * (N / (Ns * 8))));
+            const double2 w = twid<SIGN>(tw, stride * (k * (N / (Ns * 8))));
+            if (W8S) w8s[(p - 1) * blockDim.x] = w; else w8[p - 1] = w;   // only this thread reads it back
             Ns *= 8;
         }
-        if (REM == 2) {
-#pragma unroll
-            for (int b = 0; b < 2; ++b) {
-                const int j = lt + b * TPR;
-                wr[b] = twid<SIGN>(tw, stride * ((j & (Ns - 1)) * (N / (Ns * 4))));
-            }
-        } else if (REM == 1) {
-#pragma unroll
-            for (int b = 0; b < 4; ++b) {
-                const int j = lt + b * TPR;
-                wr[b] = twid<SIGN>(tw, stride * ((j & (Ns - 1)) * (N / (Ns * 2))));
-            }
-        }
+        // remainder pass: Ns = N/4 (radix 4) or N/2 (radix 2), so j = lt + b*TPR < Ns and the table
+        // index of butterfly b is simply j
+        if (REM != 0) wr0 = twid<SIGN>(tw, stride * lt);
     }
 
     // On entry v[t] = x[lt + t*TPR].  TO_SMEM: on exit the transform sits in `s` (swizzled,
@@ -141,7 +148,7 @@ struct RowFft {
                 __syncthreads();
 #pragma unroll
                 for (int t = 0; t < 8; ++t) v[t] = s[swz(lt + t * TPR)];
-                const double2 w1 = w8[p - 1];
+                const double2 w1 = W8S ? w8s[(p - 1) * blockDim.x] : w8[p - 1];
                 const double2 w2 = cmul(w1, w1), w3 = cmul(w2, w1), w4 = cmul(w2, w2);
                 v[1] = cmul(v[1], w1);
                 v[2] = cmul(v[2], w2);
@@ -170,7 +177,7 @@ struct RowFft {
                 for (int t = 0; t < 4; ++t) v[b * 4 + t] = s[swz(lt + b * TPR + t * 2 * TPR)];
 #pragma unroll
             for (int b = 0; b < 2; ++b) {
-                const double2 w1 = wr[b], w2 = cmul(w1, w1);
+                const double2 w1 = wrem(b), w2 = cmul(w1, w1);
                 v[b * 4 + 1] = cmul(v[b * 4 + 1], w1);
                 v[b * 4 + 2] = cmul(v[b * 4 + 2], w2);
                 v[b * 4 + 3] = cmul(v[b * 4 + 3], cmul(w2, w1));
@@ -192,7 +199,7 @@ struct RowFft {
             }
 #pragma unroll
             for (int b = 0; b < 4; ++b) {
-                const double2 w = cmul(v[b * 2 + 1], wr[b]);
+                const double2 w = cmul(v[b * 2 + 1], wrem(b));
                 const double2 x0 = cadd(v[b * 2], w), x1 = csub(v[b * 2], w);
                 v[b * 2] = x0;
                 v[b * 2 + 1] = x1;
@@ -682,14 +689,14 @@ template <int LOG2N>
 __global__ void __launch_bounds__(FftLaunch<LOG2N>::THREADS, FftLaunch<LOG2N>::MINB)
 k2_rfft_forward(const FftArgs a, int ngroups_per_member, int ngroups_total, int pf) {
     using L = FftLaunch<LOG2N>;
-    using F = RowFft<LOG2N, -1>;
+    using F = RowFft<LOG2N, -1, true>;
     static_assert(L::RPB == 1, "long-row path: one row per CTA");
     extern __shared__ __align__(16) double2 fft_smem[];
     constexpr int N = L::N, TPR = L::TPR, M = 2 * N;
     const int lt = threadIdx.x;
     double2* s = fft_smem;
     F fft;
-    fft.init(a.pl.tw, lt, 2);             // half-length twiddles: exp(-2 pi i n / N) = tw[2n]
+    fft.init(a.pl.tw, lt, 2, fft_smem + N);   // half-length twiddles: exp(-2 pi i n / N) = tw[2n]
     const double2 w0 = __ldg(a.pl.tw + lt);   // W^lt, W = exp(-2 pi i / M)
 
     for (int grp = blockIdx.x; grp < ngroups_total; grp += gridDim.x) {
@@ -746,13 +753,13 @@ template <int LOG2N>
 __global__ void __launch_bounds__(FftLaunch<LOG2N>::THREADS, FftLaunch<LOG2N>::MINB)
 k4_rfft_inverse(const FftArgs a, int ngroups_per_member, int ngroups_total, int pf) {
     using L = FftLaunch<LOG2N>;
-    using F = RowFft<LOG2N, +1>;
+    using F = RowFft<LOG2N, +1, true>;
     extern __shared__ __align__(16) double2 fft_smem[];
     constexpr int N = L::N, TPR = L::TPR, M = 2 * N;
     const int lt = threadIdx.x;
     double2* s = fft_smem;
     F fft;
-    fft.init(a.pl.tw, lt, 2);
+    fft.init(a.pl.tw, lt, 2, fft_smem + N);
     const double2 w0c = cconj(__ldg(a.pl.tw + lt));   // W^-lt
     const int P = a.g.P;
     const int64_t dyo = (int64_t)P * a.g.pitch;
@@ -1008,12 +1015,14 @@ template <int LOG2N, bool FWD>
 static cudaError_t launch_long(Handle* h, const FftArgs& a) {
     using L = FftLaunch<LOG2N>;
     auto kern = FWD ? k2_rfft_forward<LOG2N> : k4_rfft_inverse<LOG2N>;
+    // row buffer + the per-thread base twiddles of the radix-8 passes (RowFft<.., W8S = true>)
+    constexpr size_t smem = L::SMEM + (size_t)(LOG2N / 3 - 1) * L::THREADS * sizeof(double2);
     static bool configured = false;
     static int blocks_per_sm = 1;
     if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::SMEM);
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, kern, L::THREADS, L::SMEM);
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, kern, L::THREADS, smem);
         if (e != cudaSuccess) return e;
         if (blocks_per_sm < 1) blocks_per_sm = 1;
         configured = true;
@@ -1023,7 +1032,7 @@ static cudaError_t launch_long(Handle* h, const FftArgs& a) {
     int grid = num_sms() * blocks_per_sm;
     if (grid > total) grid = total;
     static const int pf = getenv("QG_FFT_PF") ? atoi(getenv("QG_FFT_PF")) : 1;
-    kern<<<grid, L::THREADS, L::SMEM, h->stream>>>(a, gpm, total, pf);
+    kern<<<grid, L::THREADS, smem, h->stream>>>(a, gpm, total, pf);
     return cudaGetLastError();
 }
 

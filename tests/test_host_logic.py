@@ -145,3 +145,38 @@ def test_philox_restatement_known_answer():
     assert w == [0x6627E8D5, 0xE169C58D, 0xBC57AC4C, 0x9B00DBD8]
     u = philox_ref.philox_uniform(np.arange(200000, dtype=np.uint64), 1, 99)
     assert 0.0 <= u.min() and u.max() < 1.0 and abs(u.mean() - 0.5) < 5e-3 and abs(u.var() - 1 / 12) < 2e-3
+
+
+def test_persistent_ysolve_algebra_matches_dense_cyclic_solve():
+    """The formulation of k3_ysolve_pipe - 8-row segmented zero-carry sweeps, chunk -> CTA -> cluster
+    affine closures, element-wise apply with the column-table coefficients cA / cB (tests/ysolve_model.py)
+    - against a dense solve of the cyclic tridiagonal system of src/schemes/laplacian.jl:40-58 and
+    against the recurrence form the first kernels use."""
+    import ysolve_model as ym
+    rng = np.random.default_rng(5)
+    for e, n, nctas in ((0.3, 256, 2), (2.5e-6, 512, 4), (4.61, 128, 1), (1e-3, 1024, 8)):
+        g = rng.standard_normal(n)
+        d = -(2.0 + e)
+        A = np.zeros((n, n))
+        for j in range(n):
+            A[j, j] = d
+            A[j, (j - 1) % n] += 1.0
+            A[j, (j + 1) % n] += 1.0
+        ref = np.linalg.solve(A, g)
+        u = ym.solve_cyclic_pipe(g, e, nctas)
+        tol = 1e-12 / min(1.0, e)            # the system's own conditioning ~ 4/e
+        assert np.abs(u - ref).max() <= tol * np.abs(ref).max()
+        assert np.abs(u - ym.solve_cyclic(g, e)).max() <= 1e-13 / min(1.0, e) * np.abs(ref).max()
+    # the coefficients: element-wise apply == carrying A and B through the two recurrences
+    r = 0.9
+    cA, cB = ym.column_table(r)
+    b = rng.standard_normal(32)
+    z, F, G = ym.chunk_double_sweep(b, r)
+    Ac, Bc = 0.7, -1.3
+    y = np.zeros(32); acc = Ac
+    for i in range(32):
+        acc = b[i] + r * acc; y[i] = acc
+    zz = np.zeros(32); acc = Bc
+    for i in range(31, -1, -1):
+        acc = y[i] + r * acc; zz[i] = acc
+    assert np.allclose(z + Ac * cA + Bc * cB, zz, rtol=1e-13, atol=1e-13)

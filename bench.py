@@ -73,6 +73,14 @@ class ClockSampler(threading.Thread):
     def __init__(self, index):
         super().__init__(daemon=True)
         self.index, self.stop_flag, self.samples, self.reasons, self.max_mhz = index, False, [], set(), None
+        self.ready = threading.Event()   # NVML is up (its start-up can outlast a short timed region)
+        self.active = False              # samples count only while the timed region runs
+
+    def begin(self):
+        """Start the thread, wait until NVML answers, then count samples from here on."""
+        self.start()
+        self.ready.wait(timeout=20.0)
+        self.active = True
 
     def run(self):
         try:
@@ -82,7 +90,12 @@ class ClockSampler(threading.Thread):
             self.max_mhz = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
             names = {"hw_slowdown": 0x8, "sw_power_cap": 0x4, "hw_thermal_slowdown": 0x40,
                      "sw_thermal_slowdown": 0x20, "hw_power_brake": 0x80}
+            nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)
+            self.ready.set()
             while not self.stop_flag:
+                if not self.active:
+                    time.sleep(0.001)
+                    continue
                 self.samples.append(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
                 try:
                     r = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
@@ -91,9 +104,10 @@ class ClockSampler(threading.Thread):
                 for k, bit in names.items():
                     if r & bit:
                         self.reasons.add(k)
-                time.sleep(0.02)
+                time.sleep(0.005)
         except Exception as e:   # NVML missing: report that instead of inventing numbers
             self.reasons.add(f"nvml_unavailable:{type(e).__name__}")
+            self.ready.set()
 
     def result(self):
         s = sorted(self.samples)
@@ -177,7 +191,7 @@ def run_slab(args, rank, world, local_rank, torch, dist, qgb200, np):
     sess.step(1, W)
     torch.cuda.synchronize(); dist.barrier(); torch.cuda.synchronize()
     sampler = ClockSampler(local_rank)
-    sampler.start()
+    sampler.begin()
     sess.set_profiling(True)
     l0 = sess.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -185,6 +199,7 @@ def run_slab(args, rank, world, local_rank, torch, dist, qgb200, np):
     sess.step(W + 1, K)
     e1.record(stream)
     torch.cuda.synchronize(); dist.barrier(); torch.cuda.synchronize()
+    sampler.active = False
     ms_total = e0.elapsed_time(e1)
     launches = sess.launch_count() - l0
     ktimes = sess.kernel_times()
@@ -303,7 +318,7 @@ def main():
     sess.step(1, W)
     sampler = ClockSampler(local_rank)
     barrier()
-    sampler.start()
+    sampler.begin()
     # One timed region: K steps between two events on the launching stream, with a CUDA-event pair
     # around every kernel launch inside it (qg_set_profiling; the events are read back only after
     # the region), so the per-kernel durations of the roofline come from exactly these K steps.
@@ -316,6 +331,7 @@ def main():
     sess.step(W + 1, K)
     e1.record(stream)
     barrier()
+    sampler.active = False
     ms_total = e0.elapsed_time(e1)
     launches = sess.launch_count() - l0
     ktimes = sess.kernel_times()

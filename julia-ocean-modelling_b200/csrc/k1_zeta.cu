@@ -173,7 +173,8 @@ k1_zeta_step(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ C
 template <int TY>
 static cudaError_t launch_zeta_ty(Handle* h, const ZetaArgs& a) {
     using Cfg = K1Cfg<TY>;
-    static bool attr_done = false;
+    static bool attr_done_dev[QG_MAX_DEVICES] = {};
+    bool& attr_done = attr_done_dev[dev_slot(h)];
     if (!attr_done) {
         cudaError_t e = cudaFuncSetAttribute(k1_zeta_step<TY>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM);
         if (e != cudaSuccess) return e;

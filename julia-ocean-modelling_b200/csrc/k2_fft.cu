@@ -966,8 +966,10 @@ template <int LOG2N, bool FWD>
 static cudaError_t launch_pow2(Handle* h, const FftArgs& a) {
     using L = FftLaunch<LOG2N>;
     auto kern = FWD ? k2_fft_forward<LOG2N> : k4_fft_inverse<LOG2N>;
-    static bool configured = false;
-    static int blocks_per_sm = 1;
+    static bool configured_dev[QG_MAX_DEVICES] = {};
+    static int blocks_per_sm_dev[QG_MAX_DEVICES] = {};
+    bool& configured = configured_dev[dev_slot(h)];
+    int& blocks_per_sm = blocks_per_sm_dev[dev_slot(h)];
     if (!configured) {
         if (L::SMEM > 48 * 1024) {
             cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::SMEM);
@@ -990,8 +992,10 @@ template <int LOG2N, bool FWD>
 static cudaError_t launch_r16(Handle* h, const FftArgs& a) {
     using L = Fft16Launch<LOG2N>;
     auto kern = FWD ? k2_fft16_forward<LOG2N> : k4_fft16_inverse<LOG2N>;
-    static bool configured = false;
-    static int blocks_per_sm = 1;
+    static bool configured_dev[QG_MAX_DEVICES] = {};
+    static int blocks_per_sm_dev[QG_MAX_DEVICES] = {};
+    bool& configured = configured_dev[dev_slot(h)];
+    int& blocks_per_sm = blocks_per_sm_dev[dev_slot(h)];
     if (!configured) {
         if (L::SMEM > 48 * 1024) {
             cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::SMEM);
@@ -1017,8 +1021,10 @@ static cudaError_t launch_long(Handle* h, const FftArgs& a) {
     auto kern = FWD ? k2_rfft_forward<LOG2N> : k4_rfft_inverse<LOG2N>;
     // row buffer + the per-thread base twiddles of the radix-8 passes (RowFft<.., W8S = true>)
     constexpr size_t smem = L::SMEM + (size_t)(LOG2N / 3 - 1) * L::THREADS * sizeof(double2);
-    static bool configured = false;
-    static int blocks_per_sm = 1;
+    static bool configured_dev[QG_MAX_DEVICES] = {};
+    static int blocks_per_sm_dev[QG_MAX_DEVICES] = {};
+    bool& configured = configured_dev[dev_slot(h)];
+    int& blocks_per_sm = blocks_per_sm_dev[dev_slot(h)];
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;

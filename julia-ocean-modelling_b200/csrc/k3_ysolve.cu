@@ -1066,7 +1066,8 @@ static cudaError_t launch_tma_kernel(Handle* h, const YArgs& a) {
         cfg.blockDim = dim3(((16 * pl.ts_nchunk + 31) / 32) * 32, 1, 1);
         cfg.dynamicSmemBytes = ((size_t)pl.ts_nchunk * 32 * TS_WC + 32 * TS_WC + 2 * pl.ts_nchunk * TS_LD +
                                 4 * TS_WC) * sizeof(double) + 16;
-        static size_t configured[3] = {0, 0, 0};
+        static size_t configured_dev[QG_MAX_DEVICES][3] = {};
+        size_t* configured = configured_dev[dev_slot(h)];
         auto kern = a.mode == 1 ? k3_ysolve_tma<1> : (a.mode == 2 ? k3_ysolve_tma<2> : k3_ysolve_tma<0>);
         if (cfg.dynamicSmemBytes > configured[a.mode]) {
             cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -1080,7 +1081,8 @@ static cudaError_t launch_tma_kernel(Handle* h, const YArgs& a) {
     // persistent clusters, one wave; clusters of up to 8 CTAs are portable, 16 (P > 4096) opt in
     const bool wide = pl.tp_CS > 8;
     const int csw = wide ? 16 : 8;
-    static size_t configured_p[2] = {0, 0};
+    static size_t configured_p_dev[QG_MAX_DEVICES][2] = {};
+    size_t* configured_p = configured_p_dev[dev_slot(h)];
     attr[0].val.clusterDim.x = pl.tp_CS;
     cfg.blockDim = dim3(TP_THREADS, 1, 1);
     cfg.dynamicSmemBytes = ((size_t)pl.tp_nchunk * 32 * TS_WC + 2 * CT_ROWS * TS_WC + 2 * pl.tp_nchunk * TS_LD +

@@ -244,6 +244,11 @@ struct Handle {
     int zindex(int slot, int member, int layer) const { return (slot * nm + member) * 2 + layer; }
 };
 
+// Function attributes (dynamic shared-memory opt-in, cluster size) are per device: the launchers
+// cache "already configured" per device index so that one process may hold handles on several GPUs.
+constexpr int QG_MAX_DEVICES = 64;
+inline int dev_slot(const Handle* h) { return h->device >= 0 && h->device < QG_MAX_DEVICES ? h->device : 0; }
+
 // Wraps a kernel launch.  With profiling on, a start/stop CUDA-event pair is recorded around
 // the launch on the handle's stream (no host synchronisation: the events are read back in
 // qg_kernel_times), so per-kernel durations can be taken inside a timed region.

@@ -343,3 +343,24 @@ def test_device_initial_condition_matches_host_initialise_model():
     za, pa = qgb200.run_model_no_output(mg, device_ic=7, total_steps=5)
     zb, pb = qgb200.run_model_no_output(mg, rand_fields=philox_ref.rand_fields(48, 40, 7), total_steps=5)
     assert rel(pa, pb) < TOL_FIELD and rel(za, zb) < TOL_FIELD
+
+
+@pytest.mark.gpu
+def test_two_devices_in_one_process():
+    """Handles on two GPUs held by ONE process (launch attributes are per device): same input, same
+    steps, bit-identical output; needs two visible GPUs."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    mo, mg = models(4096, 64)            # radix-16 rows, persistent y-solve
+    zeta, psi = o.initialise_model(mo, seed=2)
+    out = []
+    for dev in (0, 1):
+        z, p, f = zeta.copy(order="F"), psi.copy(order="F"), np.zeros_like(zeta)
+        with qgb200.Session(mg, device=dev) as s:
+            s.upload(z, p, f)
+            s.step(1, 4)
+            s.download(z, p, f)
+        out.append((z, p, f))
+    for a, b in zip(*out):
+        assert np.array_equal(a, b)

@@ -165,7 +165,7 @@ int64_t qg_launch_count(const qg_handle* h);
 
 /* y-slab domain decomposition of ONE run over `nranks` GPUs of a node, one process per GPU
  * (new: the reference is a single process).  Create the handle with params.P = the rank's
- * LOCAL row count (global P / nranks, a multiple of 32, <= 4096); rank r owns global rows
+ * LOCAL row count (global P / nranks, a multiple of 32, <= 8192); rank r owns global rows
  * [r * P, (r+1) * P).  After qg_dist_init every call works on the local slab: host arrays are
  * (M+2, P_local+2, 2, 3) with the neighbours' rows in the ghost rows on download, and
  * qg_step exchanges halos (ncclSend/ncclRecv ring) and the y-solve carries (ncclAllGather)

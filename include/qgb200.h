@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define QG_ABI_VERSION 1
+#define QG_ABI_VERSION 2
 
 typedef enum qg_status {
     QG_OK = 0,
@@ -167,25 +167,36 @@ int64_t qg_launch_count(const qg_handle* h);
  * (new: the reference is a single process).  Create the handle with params.P = the rank's
  * LOCAL row count (global P / nranks, a multiple of 32, <= 8192); rank r owns global rows
  * [r * P, (r+1) * P).  After qg_dist_init every call works on the local slab: host arrays are
- * (M+2, P_local+2, 2, 3) with the neighbours' rows in the ghost rows on download, and
- * qg_step exchanges halos (ncclSend/ncclRecv ring) and the y-solve carries (ncclAllGather)
- * on the handle's stream.  qg_nccl_unique_id fills a 128-byte NCCL id on one rank; the host
- * distributes it (e.g. torch.distributed / MPI broadcast) and every rank passes the same
- * bytes.  Collective: all ranks must call qg_dist_init, qg_upload_state, qg_step,
- * qg_download_state and qg_diagnostics together. */
+ * (M+2, P_local+2, 2, 3) with the neighbours' rows in the ghost rows on download.  Per step the
+ * ranks exchange two halo rows of q and of psi with their ring neighbours, the k = 0 Poisson
+ * column, the carry aggregates of the y-solve (4 x 2M doubles per rank, in place of the all-to-all
+ * transpose a tridiagonal solver would need) and the gauge constant.  After qg_dist_init alone these
+ * travel as NCCL calls on the handle's stream (send/recv ring, all-gathers, one broadcast); after
+ * qg_dist_ipc_import - the default of the host shims - the producing kernels store them straight
+ * into the other ranks' memory over NVLink and no collective call remains on the step path.
+ * qg_nccl_unique_id fills a 128-byte NCCL id on one rank; the host distributes it (e.g.
+ * torch.distributed / MPI broadcast) and every rank passes the same bytes.  Collective: all ranks
+ * must call qg_dist_init, qg_upload_state, qg_init_state, qg_step, qg_download_state and
+ * qg_diagnostics together. */
 int qg_nccl_unique_id(void* out128);
 int qg_dist_init(qg_handle* h, int rank, int nranks, const void* unique_id128);
 
-/* Optional, after qg_dist_init: exchange the per-step data over NVLink peer memory instead of NCCL
- * calls.  qg_dist_ipc_export fills 192 bytes (three CUDA IPC handles: q, psi, and the rank's
- * mailbox); the host gathers the exports of all ranks in rank order (nranks x 192 bytes) and hands
- * them to qg_dist_ipc_import on every rank.  From then on K1 / K4 store their two edge rows
- * straight into the ring neighbours' ghost rows, K2 its part of the k = 0 column into every
+/* Peer-memory exchange (optional, after qg_dist_init).  qg_dist_ipc_export fills 256 bytes: three
+ * CUDA IPC handles (q, psi, the rank's mailbox; 3 x 64 bytes), the 16-byte UUID of the rank's GPU,
+ * 48 reserved bytes.  The host gathers the exports of all ranks in rank order (nranks x 256 bytes)
+ * and hands them to qg_dist_ipc_import on every rank.  From then on K1 / K4 store their two edge
+ * rows straight into the ring neighbours' ghost rows, K2 its part of the k = 0 column into every
  * rank's gathered column, the y-solve its carry aggregates into every rank's table, rank 0 the
- * gauge, and a flag barrier (one tiny kernel, four per step) orders those stores - no collective
- * call remains on the step path.  Needs peer access between all GPUs of the run (NVSwitch). */
-int qg_dist_ipc_export(qg_handle* h, void* out192);
+ * gauge, and a flag barrier (one tiny kernel, four per step) orders those stores.  Needs peer access
+ * between all GPUs of the run (NVSwitch) and ONE RANK PER GPU: kernels that wait on one another must
+ * be resident together, so qg_dist_ipc_import returns QG_ERR_INVALID when two exports carry the same
+ * GPU UUID (qg_dist_ipc_blobs_share_device is that test, callable without a GPU) and the run stays
+ * on the NCCL path.  The barrier's wait is bounded (QG_BARRIER_TIMEOUT_S, default 120 s): if a peer
+ * never arrives every rank leaves the barrier, and the next qg_sync / qg_download_state /
+ * qg_diagnostics returns QG_ERR_CUDA with the stalled rank in qg_last_error. */
+int qg_dist_ipc_export(qg_handle* h, void* out256);
 int qg_dist_ipc_import(qg_handle* h, const void* all_ranks);
+int qg_dist_ipc_blobs_share_device(const void* all_ranks, int nranks);
 
 /* Raw device pointers for zero-copy interop (multi-GPU plumbing, torch tensors):
  * which = 0: q, 1: psi, 2: f_store, 3: spectral scratch.  Returns the base pointer, the

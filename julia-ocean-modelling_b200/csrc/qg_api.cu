@@ -34,23 +34,37 @@ static int fail(Handle* h, int code, const std::string& msg) {
 // ------------------------------------------------------------------------------------------
 // host <-> device layout conversion
 // ------------------------------------------------------------------------------------------
-// host array: (M+2, P+2, 2, 3) column-major per member, level 0 newest.
-__global__ void k_unpack(const double* __restrict__ host, double* __restrict__ dev, Geom g, int nm,
-                         int slot0, int s1, int s2) {
-    // one thread per padded device cell (ghost width 2) of one (level, member, layer) field
-    const int ix = blockIdx.x * blockDim.x + threadIdx.x - GHOST;   // -2 .. M+1
-    const int iy = blockIdx.y - GHOST;                              // -2 .. P+1
-    if (ix >= g.M + GHOST) return;
-    int z = blockIdx.z;   // (level * nm + member) * 2 + layer
-    const int layer = z & 1;
-    z >>= 1;
-    const int member = z % nm, level = z / nm;
-    const int slot = level == 0 ? slot0 : (level == 1 ? s1 : s2);
-    const int i = ((ix % g.M) + g.M) % g.M, j = ((iy % g.P) + g.P) % g.P;
-    const int64_t hs = (int64_t)(g.M + 2) * (g.P + 2);
-    const double v = host[(int64_t)member * 6 * hs + (int64_t)(level * 2 + layer) * hs +
-                          (int64_t)(j + 1) * (g.M + 2) + (i + 1)];
-    dev[((int64_t)(slot * nm + member) * 2 + layer) * g.fstride + g.at(ix, iy)] = v;
+// Host arrays are (M+2, P+2, 2, 3) column-major per member, level 0 newest, ONE ghost ring.  A host
+// field is therefore a dense (P+2) x (M+2) block, and it coincides with the sub-rectangle of the padded
+// device field that starts one ghost cell out: host [ih, jh] <-> device row YPAD-1+jh, column XPAD-1+ih.
+// Transfers are plain pitched DMA copies between the two (cudaMemcpy3DAsync, the two layers of a
+// (level, member) per call) - no staging buffer, no pack / unpack pass over the data.  What remains for
+// a kernel is the periodic ghost ring (two cells wide on the device) after an upload.
+
+// Periodic images of the interior into the ghost cells of `nz` consecutive fields
+// (update_doubly_periodic_bc!, src/schemes/boundary_conditions.jl:2-13, widened to two cells).
+// x_only = 1 (y-slab mode): only the x ghosts of the interior rows; the ghost rows belong to the ring
+// neighbours and are filled by the halo exchange.
+__global__ void k_fill_ghosts(double* __restrict__ dev, Geom g, int x_only) {
+    double* __restrict__ f = dev + (int64_t)blockIdx.y * g.fstride;
+    const int W = g.M + 2 * GHOST;
+    const int nrow = x_only ? 0 : 2 * GHOST * W;      // cells of the four ghost rows
+    const int ncol = 2 * GHOST * g.P;                 // x ghosts of the interior rows
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < nrow + ncol; e += gridDim.x * blockDim.x) {
+        int ix, iy;
+        if (e < nrow) {
+            const int rr = e / W;                      // 0..3 -> rows -2, -1, P, P+1
+            ix = e - rr * W - GHOST;
+            iy = rr < GHOST ? rr - GHOST : g.P + rr - GHOST;
+        } else {
+            const int c = e - nrow;
+            iy = c / (2 * GHOST);
+            const int cc = c - iy * 2 * GHOST;         // 0..3 -> columns -2, -1, M, M+1
+            ix = cc < GHOST ? cc - GHOST : g.M + cc - GHOST;
+        }
+        const int i = ((ix % g.M) + g.M) % g.M, j = ((iy % g.P) + g.P) % g.P;
+        f[g.at(ix, iy)] = f[g.at(i, j)];
+    }
 }
 
 __global__ void k_pack(const double* __restrict__ dev, double* __restrict__ host, Geom g, int nm,
@@ -93,31 +107,43 @@ __device__ __forceinline__ double philox_uniform(uint64_t node, uint32_t field, 
 }
 
 // psi_l = amplitude * rand at every interior node (src/model.jl:41-42); the ghost cells get the
-// periodic images (update_doubly_periodic_bc!, :44-45).  One thread per padded device cell.
-__global__ void k_ic_psi(double* __restrict__ psi, Geom g, int nm, double amplitude, uint64_t seed) {
+// periodic images (update_doubly_periodic_bc!, :44-45).  One thread per padded device cell.  The draw
+// at a node is a pure function of its GLOBAL index (row0 + j) * M + i, so a y-slab rank (row0 = first
+// global row it owns, Pglob = global row count) produces exactly its part of the single-GPU field,
+// neighbours' rows in its ghost rows included, with no exchange.
+__device__ __forceinline__ double ic_psi_at(int i, int jg, int M, uint32_t fz, double amplitude, uint64_t seed) {
+    return amplitude * philox_uniform((uint64_t)jg * M + i, fz, seed);
+}
+
+__global__ void k_ic_psi(double* __restrict__ psi, Geom g, int nm, double amplitude, uint64_t seed, int row0,
+                         int Pglob) {
     const int ix = blockIdx.x * blockDim.x + threadIdx.x - GHOST;
     const int iy = blockIdx.y - GHOST;
     if (ix >= g.M + GHOST) return;
     const int fz = blockIdx.z;   // member * 2 + layer
-    const int i = ((ix % g.M) + g.M) % g.M, j = ((iy % g.P) + g.P) % g.P;
-    const double u = philox_uniform((uint64_t)j * g.M + i, (uint32_t)fz, seed);
-    psi[(int64_t)fz * g.fstride + g.at(ix, iy)] = amplitude * u;
+    const int i = ((ix % g.M) + g.M) % g.M, jg = (((row0 + iy) % Pglob) + Pglob) % Pglob;
+    psi[(int64_t)fz * g.fstride + g.at(ix, iy)] = ic_psi_at(i, jg, g.M, (uint32_t)fz, amplitude, seed);
 }
 
 // q1 = lap(psi1) + S1 (psi2 - psi1), q2 = lap(psi2) + S2 (psi1 - psi2)  (src/model.jl:47-48,
-// laplace_5p of src/schemes/laplacian.jl:15-27), ghost images included.
-__global__ void k_ic_q(const double* __restrict__ psi, double* __restrict__ q, Geom g, int nm, double idx2,
-                       double S1, double S2) {
+// laplace_5p of src/schemes/laplacian.jl:15-27), ghost images included.  The stencil's psi values are
+// re-drawn from the counter-based generator instead of read back, so ghost rows of a y-slab (whose
+// own neighbours lie two ranks' rows away) need no halo exchange either.
+__global__ void k_ic_q(double* __restrict__ q, Geom g, int nm, double idx2, double S1, double S2,
+                       double amplitude, uint64_t seed, int row0, int Pglob) {
     const int ix = blockIdx.x * blockDim.x + threadIdx.x - GHOST;
     const int iy = blockIdx.y - GHOST;
     if (ix >= g.M + GHOST) return;
     const int fz = blockIdx.z, layer = fz & 1;
-    const int i = ((ix % g.M) + g.M) % g.M, j = ((iy % g.P) + g.P) % g.P;
-    const double* own = psi + (int64_t)fz * g.fstride;
-    const double* oth = psi + (int64_t)(fz ^ 1) * g.fstride;
-    const int64_t o = g.at(i, j);
-    const double lap = (own[o - 1] + own[o + 1] - 4.0 * own[o] + own[o - g.pitch] + own[o + g.pitch]) * idx2;
-    q[(int64_t)fz * g.fstride + g.at(ix, iy)] = lap + (layer == 0 ? S1 : S2) * (oth[o] - own[o]);
+    const int M = g.M;
+    const int i = ((ix % M) + M) % M, jg = (((row0 + iy) % Pglob) + Pglob) % Pglob;
+    const int iw = i == 0 ? M - 1 : i - 1, ie = i == M - 1 ? 0 : i + 1;
+    const int js = jg == 0 ? Pglob - 1 : jg - 1, jn = jg == Pglob - 1 ? 0 : jg + 1;
+    const uint32_t fo = (uint32_t)fz, fx = (uint32_t)(fz ^ 1);
+    const double c = ic_psi_at(i, jg, M, fo, amplitude, seed);
+    const double lap = (ic_psi_at(iw, jg, M, fo, amplitude, seed) + ic_psi_at(ie, jg, M, fo, amplitude, seed) - 4.0 * c +
+                        ic_psi_at(i, js, M, fo, amplitude, seed) + ic_psi_at(i, jn, M, fo, amplitude, seed)) * idx2;
+    q[(int64_t)fz * g.fstride + g.at(ix, iy)] = lap + (layer == 0 ? S1 : S2) * (ic_psi_at(i, jg, M, fx, amplitude, seed) - c);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -547,7 +573,7 @@ int qg_destroy(qg_handle* h) {
     if (h->copy_stream) { cudaStreamSynchronize(h->copy_stream); cudaStreamDestroy(h->copy_stream); cudaEventDestroy(h->snap_ev); }
     cudaFree(h->snap_stage);
     cudaFree(h->q); cudaFree(h->psi); cudaFree(h->f); cudaFree(h->S); cudaFree(h->k0sol);
-    cudaFree(h->scal); cudaFree(h->stage); cudaFree(h->diag_part);
+    cudaFree(h->scal); cudaFree(h->solve_tmp); cudaFree(h->diag_part);
     for (cudaEvent_t e : h->evpool) cudaEventDestroy(e);
     for (int a = 0; a < 3; ++a)
         for (int b = 0; b < 3; ++b)
@@ -557,62 +583,78 @@ int qg_destroy(qg_handle* h) {
     return QG_OK;
 }
 
-static int ensure_stage(qg_handle* h) {
-    if (h->stage) return QG_OK;
-    const size_t n = (size_t)h->nm * 6 * (h->g.M + 2) * (h->g.P + 2);
-    QG_CUDA(h, cudaMalloc((void**)&h->stage, n * sizeof(double)));
-    return QG_OK;
+// One pitched DMA copy: the two layers of (slot, member) of a device array <-> the two layers of
+// (level, member) of a host array in the reference layout.  hfields = fields per member on the host
+// (6: three levels; 2: level 1 only).
+static cudaError_t copy_fields(qg_handle* h, double* dev, int slot, double* host, int level, int member, int hfields,
+                               bool to_device, cudaStream_t st) {
+    const Geom& g = h->g;
+    const size_t hs = (size_t)(g.M + 2) * (g.P + 2);
+    cudaMemcpy3DParms p{};
+    double* d = h->field(dev, slot, member, 0) + (int64_t)(YPAD - 1) * g.pitch + (XPAD - 1);
+    double* hp = host + ((size_t)member * hfields + (size_t)level * 2) * hs;
+    const cudaPitchedPtr dptr = make_cudaPitchedPtr(d, (size_t)g.pitch * sizeof(double), (size_t)g.pitch, (size_t)g.rows);
+    const cudaPitchedPtr hptr = make_cudaPitchedPtr(hp, (size_t)(g.M + 2) * sizeof(double), (size_t)(g.M + 2), (size_t)(g.P + 2));
+    p.srcPtr = to_device ? hptr : dptr;
+    p.dstPtr = to_device ? dptr : hptr;
+    p.extent = make_cudaExtent((size_t)(g.M + 2) * sizeof(double), (size_t)(g.P + 2), 2);
+    p.kind = to_device ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToHost;
+    return cudaMemcpy3DAsync(&p, st);
 }
 
+static cudaError_t fill_ghosts(qg_handle* h, double* first_field, int nz) {
+    const int work = 2 * GHOST * (h->g.M + 2 * GHOST + h->g.P);
+    const int nb = (work + 255) / 256 < 64 ? (work + 255) / 256 : 64;
+    KernelTimer t(h, QG_K_PACK);
+    k_fill_ghosts<<<dim3(nb, nz), 256, 0, h->stream>>>(first_field, h->g, h->dist_n > 1 ? 1 : 0);
+    return cudaGetLastError();
+}
+
+// all three levels of one array; level 0 goes to slot `cur`
 static int upload_one(qg_handle* h, const double* host, double* dev, int cur) {
-    const size_t n = (size_t)h->nm * 6 * (h->g.M + 2) * (h->g.P + 2);
-    QG_CUDA(h, cudaMemcpyAsync(h->stage, host, n * sizeof(double), cudaMemcpyHostToDevice, h->stream));
-    dim3 block(128), grid((h->g.M + 2 * GHOST + 127) / 128, h->g.P + 2 * GHOST, 3 * h->nm * 2);
-    {
-        KernelTimer t(h, QG_K_PACK);
-        k_unpack<<<grid, block, 0, h->stream>>>(h->stage, dev, h->g, h->nm, cur, (cur + 2) % 3, (cur + 1) % 3);
-    }
-    QG_CUDA(h, cudaGetLastError());
+    const int slot_of[3] = {cur, (cur + 2) % 3, (cur + 1) % 3};
+    for (int level = 0; level < 3; ++level)
+        for (int m = 0; m < h->nm; ++m)
+            QG_CUDA(h, copy_fields(h, dev, slot_of[level], const_cast<double*>(host), level, m, 6, true, h->stream));
+    QG_CUDA(h, fill_ghosts(h, dev, h->nfields));
     if (h->dist_n > 1)   // y-slab: the ghost rows are the neighbours' rows, not local periodic images
         for (int s = 0; s < 3; ++s) QG_CUDA(h, dist_halo_exchange(h, dev, s));
     return QG_OK;
 }
 
-static int download_one(qg_handle* h, double* dev, double* host, int cur) {
-    const size_t n = (size_t)h->nm * 6 * (h->g.M + 2) * (h->g.P + 2);
+// needs_ghosts: the array's ghost ring is not maintained by the step kernels (f_store)
+static int download_one(qg_handle* h, double* dev, double* host, int cur, bool needs_ghosts) {
+    const int slot_of[3] = {cur, (cur + 2) % 3, (cur + 1) % 3};
+    if (needs_ghosts) QG_CUDA(h, fill_ghosts(h, dev, h->nfields));
     if (h->dist_n > 1)
         for (int s = 0; s < 3; ++s) QG_CUDA(h, dist_halo_exchange(h, dev, s));
-    dim3 block(128), grid((h->g.M + 2 + 127) / 128, h->g.P + 2, 3 * h->nm * 2);
-    {
-        KernelTimer t(h, QG_K_PACK);
-        k_pack<<<grid, block, 0, h->stream>>>(dev, h->stage, h->g, h->nm, cur, (cur + 2) % 3, (cur + 1) % 3,
-                                              h->dist_n > 1 ? 1 : 0, 6);
-    }
-    QG_CUDA(h, cudaGetLastError());
-    QG_CUDA(h, cudaMemcpyAsync(host, h->stage, n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
-    QG_CUDA(h, cudaStreamSynchronize(h->stream));
+    for (int level = 0; level < 3; ++level)
+        for (int m = 0; m < h->nm; ++m)
+            QG_CUDA(h, copy_fields(h, dev, slot_of[level], host, level, m, 6, false, h->stream));
     return QG_OK;
 }
 
 int qg_upload_state(qg_handle* h, const double* zeta, const double* psi, const double* f_store) {
     if (!h) return QG_ERR_INVALID;
     QG_CUDA(h, cudaSetDevice(h->device));
-    int rc = ensure_stage(h);
-    if (rc) return rc;
+    int rc;
     if (zeta) {
-        h->qcur = 0;
-        if ((rc = upload_one(h, zeta, h->q, 0))) return rc;
+        // zeta and f_store share one rotation counter (both are pushed by evolve_zeta!).  Uploaded
+        // together, or first, they start at slot 0; zeta alone on a handle that has stepped goes into
+        // the slots f_store's history currently occupies, so the next AB3 step still pairs them up.
+        if (f_store || !h->have_state) h->qcur = 0;
+        if ((rc = upload_one(h, zeta, h->q, h->qcur))) return rc;
         if (!f_store && !h->have_state)
             QG_CUDA(h, cudaMemsetAsync(h->f, 0, (size_t)h->nfields * h->g.fstride * sizeof(double), h->stream));
     }
     if (f_store) {
-        // f_store shares the rotation counter of zeta (both are pushed by evolve_zeta!)
         if ((rc = upload_one(h, f_store, h->f, h->qcur))) return rc;
     }
     if (psi) {
         h->pcur = 0;
         if ((rc = upload_one(h, psi, h->psi, 0))) return rc;
     }
+    h->q_halo_pending = false;
     QG_CUDA(h, cudaStreamSynchronize(h->stream));   // host buffers are borrowed only for the call
     h->have_state = true;
     return QG_OK;
@@ -620,17 +662,10 @@ int qg_upload_state(qg_handle* h, const double* zeta, const double* psi, const d
 
 // level 1 of one array only (2 fields per member), the other levels zeroed
 static int upload_level1(qg_handle* h, const double* host, double* dev) {
-    const size_t hs = (size_t)(h->g.M + 2) * (h->g.P + 2);
     QG_CUDA(h, cudaMemsetAsync(dev, 0, (size_t)h->nfields * h->g.fstride * sizeof(double), h->stream));
     for (int m = 0; m < h->nm; ++m)
-        QG_CUDA(h, cudaMemcpyAsync(h->stage + (size_t)m * 6 * hs, host + (size_t)m * 6 * hs, 2 * hs * sizeof(double),
-                                   cudaMemcpyHostToDevice, h->stream));
-    dim3 block(128), grid((h->g.M + 2 * GHOST + 127) / 128, h->g.P + 2 * GHOST, h->nm * 2);
-    {
-        KernelTimer t(h, QG_K_PACK);
-        k_unpack<<<grid, block, 0, h->stream>>>(h->stage, dev, h->g, h->nm, 0, 2, 1);
-    }
-    QG_CUDA(h, cudaGetLastError());
+        QG_CUDA(h, copy_fields(h, dev, 0, const_cast<double*>(host), 0, m, 6, true, h->stream));
+    QG_CUDA(h, fill_ghosts(h, h->field(dev, 0, 0, 0), h->nm * 2));
     if (h->dist_n > 1) QG_CUDA(h, dist_halo_exchange(h, dev, 0));
     return QG_OK;
 }
@@ -638,10 +673,10 @@ static int upload_level1(qg_handle* h, const double* host, double* dev) {
 int qg_upload_initial_state(qg_handle* h, const double* zeta, const double* psi) {
     if (!h || !zeta || !psi) return QG_ERR_INVALID;
     QG_CUDA(h, cudaSetDevice(h->device));
-    int rc = ensure_stage(h);
-    if (rc) return rc;
+    int rc;
     h->qcur = 0;
     h->pcur = 0;
+    h->q_halo_pending = false;
     if ((rc = upload_level1(h, zeta, h->q))) return rc;
     if ((rc = upload_level1(h, psi, h->psi))) return rc;
     QG_CUDA(h, cudaMemsetAsync(h->f, 0, (size_t)h->nfields * h->g.fstride * sizeof(double), h->stream));
@@ -652,7 +687,6 @@ int qg_upload_initial_state(qg_handle* h, const double* zeta, const double* psi)
 
 int qg_init_state(qg_handle* h, uint64_t seed, double amplitude, double S1, double S2) {
     if (!h) return QG_ERR_INVALID;
-    if (h->dist_n > 1) return fail(h, QG_ERR_STATE, "qg_init_state: not available in y-slab mode (upload the slab instead)");
     QG_CUDA(h, cudaSetDevice(h->device));
     const size_t bytes = (size_t)h->nfields * h->g.fstride * sizeof(double);
     QG_CUDA(h, cudaMemsetAsync(h->q, 0, bytes, h->stream));
@@ -660,17 +694,20 @@ int qg_init_state(qg_handle* h, uint64_t seed, double amplitude, double S1, doub
     QG_CUDA(h, cudaMemsetAsync(h->f, 0, bytes, h->stream));
     h->qcur = 0;
     h->pcur = 0;
+    h->q_halo_pending = false;
     dim3 block(128), grid((h->g.M + 2 * GHOST + 127) / 128, h->g.P + 2 * GHOST, h->nm * 2);
     const double inv = 1.0 / h->prm.dx;
+    // y-slab mode: this rank draws its rows of the global field (and its neighbours' rows into the ghosts)
+    const int row0 = h->dist_n > 1 ? h->dist_rank * h->g.P : 0;
     {
         KernelTimer t(h, QG_K_PACK);
-        k_ic_psi<<<grid, block, 0, h->stream>>>(h->field(h->psi, 0, 0, 0), h->g, h->nm, amplitude, seed);
+        k_ic_psi<<<grid, block, 0, h->stream>>>(h->field(h->psi, 0, 0, 0), h->g, h->nm, amplitude, seed, row0, h->Pglob);
     }
     QG_CUDA(h, cudaGetLastError());
     {
         KernelTimer t(h, QG_K_PACK);
-        k_ic_q<<<grid, block, 0, h->stream>>>(h->field(h->psi, 0, 0, 0), h->field(h->q, 0, 0, 0), h->g, h->nm, inv * inv,
-                                              S1, S2);
+        k_ic_q<<<grid, block, 0, h->stream>>>(h->field(h->q, 0, 0, 0), h->g, h->nm, inv * inv, S1, S2, amplitude, seed,
+                                              row0, h->Pglob);
     }
     QG_CUDA(h, cudaGetLastError());
     h->have_state = true;
@@ -681,12 +718,14 @@ int qg_download_state(qg_handle* h, double* zeta, double* psi, double* f_store) 
     if (!h) return QG_ERR_INVALID;
     if (!h->have_state) return fail(h, QG_ERR_STATE, "qg_download_state: no state uploaded");
     QG_CUDA(h, cudaSetDevice(h->device));
-    int rc = ensure_stage(h);
-    if (rc) return rc;
-    if (zeta && (rc = download_one(h, h->q, zeta, h->qcur))) return rc;
-    if (psi && (rc = download_one(h, h->psi, psi, h->pcur))) return rc;
-    if (f_store && (rc = download_one(h, h->f, f_store, h->qcur))) return rc;
-    return QG_OK;
+    int rc;
+    // q and psi carry their periodic ghost ring on the device (written by K1 / K4 with every step);
+    // f_store's is produced here.  The copies run back to back on the handle's stream.
+    if (zeta && (rc = download_one(h, h->q, zeta, h->qcur, false))) return rc;
+    if (psi && (rc = download_one(h, h->psi, psi, h->pcur, false))) return rc;
+    if (f_store && (rc = download_one(h, h->f, f_store, h->qcur, true))) return rc;
+    QG_CUDA(h, cudaStreamSynchronize(h->stream));
+    return dist_poll_error(h);
 }
 
 // Snapshot of the newest level (src/run_model.jl:70-73, 86-90 write exactly zeta[:,:,:,1] and
@@ -827,7 +866,7 @@ int qg_sync(qg_handle* h) {
     QG_CUDA(h, cudaSetDevice(h->device));
     QG_CUDA(h, cudaStreamSynchronize(h->stream));
     QG_CUDA(h, cudaGetLastError());
-    return QG_OK;
+    return dist_poll_error(h);
 }
 
 int qg_diagnostics(qg_handle* h, double* energy, double* enstrophy) {
@@ -841,6 +880,7 @@ int qg_diagnostics(qg_handle* h, double* energy, double* enstrophy) {
     QG_CUDA(h, cudaMemcpyAsync(out.data(), h->diag_part + (int64_t)h->nm * h->diag_blocks * 2,
                                out.size() * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
     QG_CUDA(h, cudaStreamSynchronize(h->stream));
+    if (int rc = dist_poll_error(h)) return rc;
     for (int m = 0; m < h->nm; ++m) {
         energy[m] = out[2 * m];
         enstrophy[m] = out[2 * m + 1];
@@ -850,27 +890,20 @@ int qg_diagnostics(qg_handle* h, double* energy, double* enstrophy) {
 
 int qg_solve(qg_handle* h, int pinned, const double* f, double* u) {
     if (!h || !f || !u) return QG_ERR_INVALID;
+    if (h->dist_n > 1) return fail(h, QG_ERR_STATE, "qg_solve: not available on a y-slab handle");
+    if (!h->plan_ok) return fail(h, QG_ERR_STATE, "qg_solve: the handle has no plan");
     QG_CUDA(h, cudaSetDevice(h->device));
-    int rc = ensure_stage(h);
-    if (rc) return rc;
-    // Scratch: slot (qcur+1)%3 of q (the oldest PV level, about to be overwritten by the next
-    // evolve_zeta anyway) would clobber downloadable history, so use the spectral scratch path
-    // on dedicated temporaries instead.
     const Geom& g = h->g;
-    const size_t hn = (size_t)(g.M + 2) * (g.P + 2);
-    double* tmp = nullptr;   // two padded fields in, two out
-    QG_CUDA(h, cudaMalloc((void**)&tmp, 4 * g.fstride * sizeof(double)));
-    std::vector<double> hostbuf((size_t)h->nm * 6 * hn, 0.0);
-    // level 0, layers 0 and 1 of member 0 both carry f: field 1 solves Poisson, field 2 Helmholtz
-    memcpy(hostbuf.data(), f, hn * sizeof(double));
-    memcpy(hostbuf.data() + hn, f, hn * sizeof(double));
-    cudaError_t e = cudaMemcpyAsync(h->stage, hostbuf.data(), 2 * hn * sizeof(double), cudaMemcpyHostToDevice, h->stream);
-    if (e == cudaSuccess) {
-        dim3 block(128), grid((g.M + 2 * GHOST + 127) / 128, g.P + 2 * GHOST, 2);
-        KernelTimer t(h, QG_K_PACK);
-        k_unpack<<<grid, block, 0, h->stream>>>(h->stage, tmp, g, 1, 0, 0, 0);
-        e = cudaGetLastError();
-    }
+    // Four padded fields of its own (two in, two out), kept on the handle: the state arrays stay untouched.
+    if (!h->solve_tmp) QG_CUDA(h, cudaMalloc((void**)&h->solve_tmp, 4 * g.fstride * sizeof(double)));
+    double* tmp = h->solve_tmp;
+    // both layers carry f: field 1 solves Poisson, field 2 Helmholtz
+    cudaError_t e = cudaSuccess;
+    for (int l = 0; l < 2 && e == cudaSuccess; ++l)
+        e = cudaMemcpy2DAsync(tmp + l * g.fstride + (int64_t)(YPAD - 1) * g.pitch + (XPAD - 1), (size_t)g.pitch * sizeof(double), f,
+                              (size_t)(g.M + 2) * sizeof(double), (size_t)(g.M + 2) * sizeof(double), (size_t)(g.P + 2),
+                              cudaMemcpyHostToDevice, h->stream);
+    if (e == cudaSuccess) e = fill_ghosts(h, tmp, 2);
     // identity projections: psi~ = solve(f) per field
     qg_params saved = h->prm;
     const double I4[4] = {1.0, 0.0, 0.0, 1.0};
@@ -881,18 +914,14 @@ int qg_solve(qg_handle* h, int pinned, const double* f, double* u) {
     if (e == cudaSuccess) e = launch_fft_forward(h, tmp, 0);
     if (e == cudaSuccess) e = launch_ysolve(h, pinned ? 1 : 0, 0);
     if (e == cudaSuccess) e = launch_fft_inverse(h, tmp + 2 * g.fstride, pinned ? 1 : 0);
-    if (e == cudaSuccess) {
-        dim3 block(128), grid((g.M + 2 + 127) / 128, g.P + 2, 2);
-        KernelTimer t(h, QG_K_PACK);
-        k_pack<<<grid, block, 0, h->stream>>>(tmp + 2 * g.fstride, h->stage, g, 1, 0, 0, 0, 0, 6);
-        e = cudaGetLastError();
-    }
     if (e == cudaSuccess)
-        e = cudaMemcpyAsync(u, h->stage + (pinned ? 0 : hn), hn * sizeof(double), cudaMemcpyDeviceToHost, h->stream);
+        e = cudaMemcpy2DAsync(u, (size_t)(g.M + 2) * sizeof(double),
+                              tmp + (2 + (pinned ? 0 : 1)) * g.fstride + (int64_t)(YPAD - 1) * g.pitch + (XPAD - 1),
+                              (size_t)g.pitch * sizeof(double), (size_t)(g.M + 2) * sizeof(double), (size_t)(g.P + 2),
+                              cudaMemcpyDeviceToHost, h->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
     h->nm = nm_saved;
     h->prm = saved;
-    cudaFree(tmp);
     QG_CUDA(h, e);
     return QG_OK;
 }
@@ -925,10 +954,15 @@ int qg_dist_init(qg_handle* h, int rank, int nranks, const void* unique_id128) {
     return QG_OK;
 }
 
-int qg_dist_ipc_export(qg_handle* h, void* out192) {
-    if (!h || !out192) return QG_ERR_INVALID;
+int qg_dist_ipc_export(qg_handle* h, void* out256) {
+    if (!h || !out256) return QG_ERR_INVALID;
     QG_CUDA(h, cudaSetDevice(h->device));
-    return dist_ipc_export(h, out192);
+    return dist_ipc_export(h, out256);
+}
+
+int qg_dist_ipc_blobs_share_device(const void* all_ranks, int nranks) {
+    if (!all_ranks || nranks < 1 || nranks > 8) return QG_ERR_INVALID;
+    return dist_blobs_share_device(all_ranks, nranks);
 }
 
 int qg_dist_ipc_import(qg_handle* h, const void* all_ranks) {

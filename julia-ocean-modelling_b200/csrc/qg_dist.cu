@@ -74,12 +74,17 @@ static cudaError_t nccl_check(Handle* h, ncclResult_t r, const char* what) {
     return cudaErrorUnknown;
 }
 
-// Developer diagnostic: QG_DIST_SKIP=<mask> drops collectives (1 halo ring, 2 all-gather, 4 broadcast)
-// to expose their cost in a timing run; results are then wrong by construction.
+// Developer builds only (-DQG_DEV): QG_DIST_SKIP=<mask> drops collectives (1 halo ring, 2 all-gather,
+// 4 broadcast) to expose their cost in a timing run; results are then wrong by construction, so the
+// switch does not exist in the shipped library.
+#ifdef QG_DEV
 static int skip_mask() {
     static const int m = getenv("QG_DIST_SKIP") ? atoi(getenv("QG_DIST_SKIP")) : 0;
     return m;
 }
+#else
+static constexpr int skip_mask() { return 0; }
+#endif
 
 cudaError_t dist_allgather(Handle* h, const double* send, double* recv, size_t count) {
     if (skip_mask() & 2) return cudaSuccess;
@@ -136,16 +141,60 @@ struct PeerFlags {
     unsigned long long* f[8];
 };
 
-__global__ void k_xgpu_barrier(PeerFlags p, int rank, int n, unsigned long long epoch) {
+// Layout of the first 256 doubles of a mailbox, as 64-bit words: word r * 16 = the epoch rank r has
+// reached (one 128-byte line per writer), word MB_ABORT = sticky abort word (0 = healthy).
+constexpr int MB_ABORT = 200;
+
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long global_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+
+// The wait is bounded: a rank that does not see every peer's epoch within `timeout_ns` (a dead peer, or
+// ranks whose call sequences diverged) writes the abort word of EVERY rank and leaves; a set abort word
+// ends this and every later barrier at once, so no GPU is ever left in an unkillable spin.  The host
+// reads the word after its next stream synchronisation (dist_poll_error) and reports QG_ERR_CUDA.
+// One rank per GPU is a precondition (qg_dist_ipc_import refuses anything else): kernels that wait on
+// one another must be resident at the same time.
+__global__ void k_xgpu_barrier(PeerFlags p, int rank, int n, unsigned long long epoch, unsigned long long timeout_ns) {
     const int i = threadIdx.x;
-    if (i < n) {
-        __threadfence_system();
-        asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p.f[i] + rank * 16), "l"(epoch) : "memory");
-        unsigned long long v;
-        do {
-            asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p.f[rank] + i * 16) : "memory");
-        } while (v < epoch);
+    if (i >= n) return;
+    unsigned long long* mine = p.f[rank];
+    if (ld_acquire_sys(mine + MB_ABORT) != 0ull) return;
+    __threadfence_system();
+    st_release_sys(p.f[i] + rank * 16, epoch);
+    const unsigned long long t0 = global_ns();
+    unsigned int backoff = 32;
+    while (ld_acquire_sys(mine + i * 16) < epoch) {
+        if (ld_acquire_sys(mine + MB_ABORT) != 0ull) return;
+        if (global_ns() - t0 > timeout_ns) {
+            // word = epoch that failed (never 0: epochs start at 1), high bits = the rank that never arrived
+            const unsigned long long w = epoch | ((unsigned long long)(i + 1) << 56);
+            for (int r = 0; r < n; ++r) st_release_sys(p.f[r] + MB_ABORT, w);
+            return;
+        }
+        __nanosleep(backoff);
+        if (backoff < 1024) backoff <<= 1;
     }
+}
+
+static unsigned long long barrier_timeout_ns() {
+    static const unsigned long long t = [] {
+        const char* v = getenv("QG_BARRIER_TIMEOUT_S");
+        double s = v ? atof(v) : 120.0;
+        if (!(s > 0.0)) s = 120.0;
+        return (unsigned long long)(s * 1e9);
+    }();
+    return t;
 }
 
 cudaError_t dist_barrier(Handle* h) {
@@ -154,11 +203,41 @@ cudaError_t dist_barrier(Handle* h) {
     ++h->epoch;
     h->launches++;
     h->q_halo_pending = false;
-    k_xgpu_barrier<<<1, 32, 0, h->stream>>>(p, h->dist_rank, h->dist_n, h->epoch);
+    k_xgpu_barrier<<<1, 32, 0, h->stream>>>(p, h->dist_rank, h->dist_n, h->epoch, barrier_timeout_ns());
     return cudaGetLastError();
 }
 
-int dist_ipc_export(Handle* h, void* out192) {
+// After a stream synchronisation: has a cross-GPU barrier of this run given up?  (peer mode only)
+int dist_poll_error(Handle* h) {
+    if (!h->peer_ok || !h->mailbox) return QG_OK;
+    unsigned long long w = 0;
+    cudaError_t e = cudaMemcpy(&w, reinterpret_cast<unsigned long long*>(h->mailbox) + MB_ABORT, sizeof(w), cudaMemcpyDeviceToHost);
+    if (e != cudaSuccess) { h->err = std::string("reading the barrier status: ") + cudaGetErrorString(e); return QG_ERR_CUDA; }
+    if (w == 0) return QG_OK;
+    char b[256];
+    snprintf(b, sizeof(b), "cross-GPU barrier %llu timed out waiting for rank %d (a peer died, or the ranks did not make the "
+             "same sequence of collective calls); the state of this run is invalid", w & 0x00ffffffffffffffull, (int)(w >> 56) - 1);
+    h->err = b;
+    return QG_ERR_CUDA;
+}
+
+// ---- IPC blobs -----------------------------------------------------------------------------------
+// One export = 256 bytes: three CUDA IPC handles (q, psi, mailbox; 3 x 64 bytes), the 16-byte UUID of the
+// exporting GPU, 48 bytes reserved (zero).
+constexpr int IPC_BLOB = 256;
+
+// 1 if two of the `nranks` exports in `all` come from the same GPU (equal UUIDs), else 0.  Two ranks on
+// one GPU must never use the flag barrier: their barrier kernels are not guaranteed to be resident at
+// the same time (B200_PROFILING.md: Xid 109).
+int dist_blobs_share_device(const void* all, int nranks) {
+    const unsigned char* b = static_cast<const unsigned char*>(all);
+    for (int i = 0; i < nranks; ++i)
+        for (int j = i + 1; j < nranks; ++j)
+            if (memcmp(b + (size_t)i * IPC_BLOB + 192, b + (size_t)j * IPC_BLOB + 192, 16) == 0) return 1;
+    return 0;
+}
+
+int dist_ipc_export(Handle* h, void* out256) {
     if (h->dist_n < 2 || !h->mailbox) { h->err = "qg_dist_ipc_export: call qg_dist_init first"; return QG_ERR_STATE; }
     static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
     cudaIpcMemHandle_t hd[3];
@@ -167,25 +246,50 @@ int dist_ipc_export(Handle* h, void* out192) {
         cudaError_t e = cudaIpcGetMemHandle(&hd[i], ptr[i]);
         if (e != cudaSuccess) { h->err = std::string("cudaIpcGetMemHandle: ") + cudaGetErrorString(e); return QG_ERR_CUDA; }
     }
-    memcpy(out192, hd, sizeof(hd));
+    cudaDeviceProp prop;
+    cudaError_t e = cudaGetDeviceProperties(&prop, h->device);
+    if (e != cudaSuccess) { h->err = std::string("cudaGetDeviceProperties: ") + cudaGetErrorString(e); return QG_ERR_CUDA; }
+    static_assert(sizeof(prop.uuid) == 16, "cudaUUID_t is 16 bytes");
+    unsigned char* out = static_cast<unsigned char*>(out256);
+    memset(out, 0, IPC_BLOB);
+    memcpy(out, hd, sizeof(hd));
+    memcpy(out + 192, &prop.uuid, 16);
     return QG_OK;
 }
 
 int dist_ipc_import(Handle* h, const void* all) {
     if (h->dist_n < 2 || !h->mailbox) { h->err = "qg_dist_ipc_import: call qg_dist_init first"; return QG_ERR_STATE; }
     if (h->peer_ok) return QG_OK;
-    const cudaIpcMemHandle_t* hd = static_cast<const cudaIpcMemHandle_t*>(all);
+    if (dist_blobs_share_device(all, h->dist_n)) {
+        h->err = "qg_dist_ipc_import: two ranks of this run share a GPU; the peer-memory flag barrier needs one rank per "
+                 "GPU (the run stays on the NCCL exchange path)";
+        return QG_ERR_INVALID;
+    }
+    const unsigned char* blobs = static_cast<const unsigned char*>(all);
+    auto close_all = [&]() {   // undo a partial import
+        for (int r = 0; r < h->dist_n; ++r) {
+            if (r == h->dist_rank) continue;
+            if (h->peer_q[r]) cudaIpcCloseMemHandle(h->peer_q[r]);
+            if (h->peer_psi[r]) cudaIpcCloseMemHandle(h->peer_psi[r]);
+            if (h->peer_mail[r]) cudaIpcCloseMemHandle(h->peer_mail[r]);
+        }
+        for (int r = 0; r < 8; ++r) h->peer_q[r] = h->peer_psi[r] = h->peer_mail[r] = nullptr;
+    };
     for (int r = 0; r < h->dist_n; ++r) {
         if (r == h->dist_rank) {
             h->peer_q[r] = h->q; h->peer_psi[r] = h->psi; h->peer_mail[r] = h->mailbox;
             continue;
         }
+        cudaIpcMemHandle_t hd[3];
+        memcpy(hd, blobs + (size_t)r * IPC_BLOB, sizeof(hd));
         double** dst[3] = {&h->peer_q[r], &h->peer_psi[r], &h->peer_mail[r]};
         for (int i = 0; i < 3; ++i) {
             void* p = nullptr;
-            cudaError_t e = cudaIpcOpenMemHandle(&p, hd[3 * r + i], cudaIpcMemLazyEnablePeerAccess);
+            cudaError_t e = cudaIpcOpenMemHandle(&p, hd[i], cudaIpcMemLazyEnablePeerAccess);
             if (e != cudaSuccess) {
                 h->err = std::string("cudaIpcOpenMemHandle (is NVLink peer access available?): ") + cudaGetErrorString(e);
+                cudaGetLastError();
+                close_all();
                 return QG_ERR_CUDA;
             }
             *dst[i] = static_cast<double*>(p);

@@ -148,13 +148,12 @@ cudaError_t dist_broadcast(Handle* h, double* buf, size_t count, int root);
 cudaError_t dist_allreduce_sum(Handle* h, double* buf, size_t count);
 void dist_destroy(Handle* h);
 cudaError_t dist_barrier(Handle* h);                       // cross-GPU flag barrier on the handle's stream (peer mode)
-int dist_ipc_export(Handle* h, void* out192);
+int dist_ipc_export(Handle* h, void* out256);
 int dist_ipc_import(Handle* h, const void* all);
+int dist_blobs_share_device(const void* all, int nranks);  // two exports from one GPU?
+int dist_poll_error(Handle* h);                            // after a stream sync: did a flag barrier give up?
 int dist_init(Handle* h, int rank, int nranks, const void* id128);
 int dist_unique_id(void* out128, std::string* err);
-cudaError_t launch_unpack(Handle* h, const double* host_like, double* dev_fields, int slot_of_level0,
-                          int nlevels);
-cudaError_t launch_pack(Handle* h, const double* dev_fields, double* host_like, int cur);
 cudaError_t launch_diag(Handle* h);
 cudaError_t build_plan(Handle* h);
 void free_plan(Handle* h);
@@ -181,7 +180,7 @@ struct Handle {
     double* S = nullptr;             // spectral scratch [nm][P][2M]
     double* k0sol = nullptr;         // [nm][P]
     double* scal = nullptr;          // [nm][4]
-    double* stage = nullptr;         // host-layout staging (3*2*(M+2)*(P+2)*nm doubles)
+    double* solve_tmp = nullptr;     // qg_solve: four padded fields (two in, two out)
     double* snap_stage = nullptr;    // snapshot staging: level 1 of zeta and of psi (qg_snapshot_begin)
     cudaStream_t copy_stream = nullptr;
     cudaEvent_t snap_ev = nullptr;

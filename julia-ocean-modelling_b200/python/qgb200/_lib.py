@@ -60,6 +60,7 @@ SYMBOLS = {
     "qg_dist_init": (C.c_int, [_P, C.c_int, C.c_int, _P]),
     "qg_dist_ipc_export": (C.c_int, [_P, _P]),
     "qg_dist_ipc_import": (C.c_int, [_P, _P]),
+    "qg_dist_ipc_blobs_share_device": (C.c_int, [_P, C.c_int]),
     "qg_device_layout": (C.c_int, [_P, C.c_int, C.POINTER(_P), C.POINTER(C.c_int64),
                                    C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
 }

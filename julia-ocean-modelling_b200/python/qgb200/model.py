@@ -209,15 +209,23 @@ class Session:
         assert len(unique_id) == 128
         self._ck(self._lib.qg_dist_init(self._h, int(rank), int(nranks), C.c_char_p(unique_id)))
 
+    IPC_BLOB = 256
+
     def dist_peer_init(self, allgather):
         """Switch the per-step exchanges of a y-slab run from NCCL calls to NVLink peer stores
         (qg_dist_ipc_export / qg_dist_ipc_import).  `allgather(bytes) -> list[bytes]` gathers one
-        192-byte blob per rank in rank order (e.g. torch.distributed.all_gather_object)."""
-        buf = C.create_string_buffer(192)
+        256-byte blob per rank in rank order (e.g. torch.distributed.all_gather_object).  Returns
+        True when the peer path is active, False when the library refused it because two ranks
+        share a GPU (the flag barrier needs one rank per GPU): the run then stays on NCCL."""
+        buf = C.create_string_buffer(self.IPC_BLOB)
         self._ck(self._lib.qg_dist_ipc_export(self._h, buf))
         blobs = list(allgather(buf.raw))
-        assert all(len(b) == 192 for b in blobs)
-        self._ck(self._lib.qg_dist_ipc_import(self._h, C.c_char_p(b"".join(blobs))))
+        assert all(len(b) == self.IPC_BLOB for b in blobs)
+        allb = b"".join(blobs)
+        if self._lib.qg_dist_ipc_blobs_share_device(C.c_char_p(allb), len(blobs)) == 1:
+            return False
+        self._ck(self._lib.qg_dist_ipc_import(self._h, C.c_char_p(allb)))
+        return True
 
     # -- state transfer -----------------------------------------------------------------
     def upload(self, zeta=None, psi=None, f_store=None):

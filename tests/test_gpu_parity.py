@@ -9,6 +9,7 @@ import numpy as np
 import pytest
 
 import qg_oracle as o
+import qg_oracle_c as oc
 import qgb200
 
 pytestmark = pytest.mark.gpu
@@ -196,12 +197,13 @@ def test_headline_grid_properties_4096():
       - the pinned unknown psi~1(0,0) is zero;
       - PV is conserved by the flux-form RHS: sum(q+ - q) / (sum |q| ) is round-off for layer 1
         (layer 2 has the r*Lap(psi) sink whose sum is also zero on a periodic grid);
-      - against the spectral oracle for 3 steps (Euler, Euler, AB3) to <= 1e-10."""
+      - against the oracle (C restatement, itself pinned to the NumPy one in tests/test_oracle_c.py) for
+        the 10 steps north_star names (2 Euler + 8 AB3): psi, q and the RHS history to <= 1e-10."""
     M = P = 4096
     mo, mg = models(M, P, dt=300.0)
     zeta, psi = o.initialise_model(mo, seed=1)
     f = np.zeros_like(zeta)
-    z, p, ff, E, Z = gpu_run(mg, zeta, psi, f, 1, 3)
+    z, p, ff, E, Z = gpu_run(mg, zeta, psi, f, 1, 10)
     Pinv = o.P_inv_matrix(mo)
     q = z[1:-1, 1:-1, :, 0]
     qt = [Pinv[i, 0] * q[:, :, 0] + Pinv[i, 1] * q[:, :, 1] for i in range(2)]
@@ -219,11 +221,52 @@ def test_headline_grid_properties_4096():
     for l in range(2):
         dq = (z[1:-1, 1:-1, l, 0] - z[1:-1, 1:-1, l, 1]).sum()
         assert abs(dq) / np.abs(z[1:-1, 1:-1, l, 0]).sum() < 1e-11
-    o.run_steps(mo, zeta, psi, f, o.make_factors(mo, "spectral"), 1, 3)
-    assert rel(p[:, :, :, 0], psi[:, :, :, 0]) < TOL_FIELD
-    assert rel(z[:, :, :, 0], zeta[:, :, :, 0]) < TOL_FIELD
+    oc.run_steps(mo, zeta, psi, f, 1, 10)
+    for lvl in range(3):
+        assert rel(p[:, :, :, lvl], psi[:, :, :, lvl]) < TOL_FIELD
+        assert rel(z[:, :, :, lvl], zeta[:, :, :, lvl]) < TOL_FIELD
+        assert rel(ff[:, :, :, lvl], f[:, :, :, lvl]) < TOL_FIELD
     Eo, Zo = o.diagnostics(mo, zeta, psi)
     assert abs(E - Eo) / Eo < TOL_DIAG and abs(Z - Zo) / Zo < TOL_DIAG
+
+
+def test_energy_enstrophy_after_1000_steps_1024():
+    """SURVEY.md 8(d) correctness gate at config 2's grid: domain-integrated energy and enstrophy after
+    1000 steps of 1024 x 1024 (dt = 30 min) <= 1e-8 relative against the oracle (C restatement), and the
+    fields themselves, which stay far inside the 10-step tolerance."""
+    mo, mg = models(1024, 1024, dt=1800.0)
+    zeta, psi = o.initialise_model(mo, seed=1)
+    f = np.zeros_like(zeta)
+    with qgb200.Session(mg) as s:
+        s.upload_initial(zeta, psi)
+        s.step(1, 1000)
+        z, p = s.new_state_array(), s.new_state_array()
+        s.download(zeta=z, psi=p)
+        E, Z = s.diagnostics()
+    oc.run_steps(mo, zeta, psi, f, 1, 1000)
+    Eo, Zo = o.diagnostics(mo, zeta, psi)
+    assert abs(E - Eo) / Eo < TOL_DIAG and abs(Z - Zo) / Zo < TOL_DIAG, (E, Eo, Z, Zo)
+    assert rel(p[:, :, :, 0], psi[:, :, :, 0]) < 1e-9 and rel(z[:, :, :, 0], zeta[:, :, :, 0]) < 1e-9
+
+
+def test_reupload_of_zeta_and_psi_keeps_the_rhs_history():
+    """qg_upload_state(zeta, psi, NULL) on a handle that has stepped: f_store stays on the device
+    ("NULL leaves that array untouched") and must still line up with the freshly uploaded zeta, so
+    the next AB3 step reads the right two older right-hand sides."""
+    mo, mg = models(40, 24)
+    zeta, psi = o.initialise_model(mo, seed=5)
+    f = np.zeros_like(zeta)
+    fac = o.make_factors(mo, "direct")
+    with qgb200.Session(mg) as s:
+        s.upload(zeta, psi, f)
+        s.step(1, 5)
+        z, p = s.new_state_array(), s.new_state_array()
+        s.download(zeta=z, psi=p)
+        s.upload(z, p, None)            # zeta and psi only
+        s.step(6, 3)
+        s.download(zeta=z, psi=p)
+    o.run_steps(mo, zeta, psi, f, fac, 1, 8)
+    assert rel(p, psi) < TOL_FIELD and rel(z, zeta) < TOL_FIELD
 
 
 def test_error_reporting():

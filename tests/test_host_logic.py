@@ -34,7 +34,26 @@ def test_library_exports_every_declared_symbol():
     for n in names:
         assert hasattr(lib, n), f"libqgb200.so does not export {n}"
     assert sorted(_lib.SYMBOLS) == names, "python binding table and header disagree"
-    assert qgb200.load().qg_abi_version() == 1
+    assert qgb200.load().qg_abi_version() == 2
+
+
+def test_peer_exchange_is_refused_when_two_ranks_share_a_gpu():
+    """qg_dist_ipc_import's precondition, checked without a GPU: exports (3 IPC handles + the GPU's
+    UUID at byte 192, 256 bytes per rank) from the same device must be refused - two flag-waiting
+    barrier kernels on one GPU are not guaranteed to be co-resident (B200_PROFILING.md, Xid 109)."""
+    _ensure_built()
+    lib = qgb200.load()
+    blob = lambda uuid: bytes(192) + bytes(uuid) + bytes(48)
+    u = [bytes([r + 1] * 16) for r in range(8)]
+    distinct = b"".join(blob(x) for x in u)
+    assert lib.qg_dist_ipc_blobs_share_device(distinct, 8) == 0
+    assert lib.qg_dist_ipc_blobs_share_device(distinct, 2) == 0
+    for n, dup in ((2, (0, 1)), (4, (1, 3)), (8, (0, 7))):
+        v = list(u[:n])
+        v[dup[1]] = v[dup[0]]
+        assert lib.qg_dist_ipc_blobs_share_device(b"".join(blob(x) for x in v), n) == 1
+    assert lib.qg_dist_ipc_blobs_share_device(None, 2) == -1 and lib.qg_dist_ipc_blobs_share_device(distinct, 9) == -1
+    assert qgb200.Session.IPC_BLOB == 256
 
 
 def test_param_struct_matches_header_layout():

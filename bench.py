@@ -322,11 +322,11 @@ def slab_session(torch, dist, qgb200, stream, local_rank, rank, world, M, P):
     return sess, glob, a, peer
 
 
-def slab_parity_leg(torch, dist, qgb200, np, stream, local_rank, rank, world, steps=10):
+def slab_parity_leg(torch, dist, qgb200, np, stream, local_rank, rank, world, steps=10, grid=None):
     """A y-slab run of SLAB_PARITY_GRID against the C oracle's solution of the GLOBAL problem.
     Rank 0 draws the same device initial condition on a single-GPU handle, downloads it, lets the
     oracle step it on the host, and broadcasts the result; every rank compares its slab."""
-    M, P = SLAB_PARITY_GRID
+    M, P = grid or SLAB_PARITY_GRID
     o, oc = oracle_modules()
     sess, glob, a, peer = slab_session(torch, dist, qgb200, stream, local_rank, rank, world, M, P)
     shape = (M + 2, P + 2, 2)

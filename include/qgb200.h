@@ -144,6 +144,12 @@ int qg_sync(qg_handle* h);
  * (definition: DESIGN.md "Diagnostics"; the reference has none). */
 int qg_diagnostics(qg_handle* h, double* energy, double* enstrophy);
 
+/* Extrema of the newest level over the interior, per member: out[8 * member + ..] = {max q_1, min q_1,
+ * max q_2, min q_2, max psi_1, min psi_1, max psi_2, min psi_2}.  Device-side counterpart of the
+ * reference's update_max / update_min (src/run_model.jl:41-53), which scan a host matrix; the host
+ * shims keep the running maximum / minimum.  y-slab mode: extrema of the whole domain (collective). */
+int qg_extrema(qg_handle* h, double* out);
+
 /* Single-use solves of src/schemes/laplacian.jl:78-111 on the plan of this handle:
  * sp_solve_poisson (pinned = 1, alpha ignored: uses the Poisson plan) or
  * sp_solve_modified_helmholtz with the handle's alpha (pinned = 0).

@@ -194,6 +194,60 @@ k5_diag_final(const double* __restrict__ part, int nb, double scale, double* __r
     }
 }
 
+// Running extrema (the reference's update_max / update_min, src/run_model.jl:41-53, which scan a whole
+// matrix on the host): max and min over the interior of q_1, q_2, psi_1, psi_2 of the newest level.
+// out[member][8] = {max q1, min q1, max q2, min q2, max psi1, min psi1, max psi2, min psi2}; stage 1 leaves
+// one row per block with the minima NEGATED so that both stages (and the y-slab all-reduce) are a max.
+__device__ __forceinline__ double block_max(double v, double* sh) {
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+    __syncthreads();
+    if (lane == 0) sh[w] = v;
+    __syncthreads();
+    v = lane < nw ? sh[lane] : -INFINITY;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+__global__ void __launch_bounds__(256)
+k5_extrema_partial(const double* __restrict__ q, const double* __restrict__ psi, Geom g, double* __restrict__ part) {
+    __shared__ double sh[32];
+    const int member = blockIdx.y;
+    const double* __restrict__ fld[4] = {q + (int64_t)member * 2 * g.fstride, q + (int64_t)(member * 2 + 1) * g.fstride,
+                                         psi + (int64_t)member * 2 * g.fstride, psi + (int64_t)(member * 2 + 1) * g.fstride};
+    double m[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) m[k] = -INFINITY;
+    for (int j = blockIdx.x; j < g.P; j += gridDim.x)
+        for (int i = threadIdx.x; i < g.M; i += blockDim.x) {
+            const int64_t o = g.at(i, j);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const double v = fld[k][o];
+                m[2 * k] = fmax(m[2 * k], v);
+                m[2 * k + 1] = fmax(m[2 * k + 1], -v);
+            }
+        }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const double r = block_max(m[k], sh);
+        if (threadIdx.x == 0) part[((int64_t)member * gridDim.x + blockIdx.x) * 8 + k] = r;
+    }
+}
+
+__global__ void __launch_bounds__(256) k5_extrema_final(const double* __restrict__ part, int nb, double* __restrict__ out) {
+    __shared__ double sh[32];
+    const int member = blockIdx.x;
+    for (int k = 0; k < 8; ++k) {
+        double m = -INFINITY;
+        for (int b = threadIdx.x; b < nb; b += blockDim.x) m = fmax(m, part[((int64_t)member * nb + b) * 8 + k]);
+        m = block_max(m, sh);
+        if (threadIdx.x == 0) out[member * 8 + k] = m;   // minima still negated
+    }
+}
+
 // ------------------------------------------------------------------------------------------
 // spectral plan
 // ------------------------------------------------------------------------------------------
@@ -573,7 +627,7 @@ int qg_destroy(qg_handle* h) {
     if (h->copy_stream) { cudaStreamSynchronize(h->copy_stream); cudaStreamDestroy(h->copy_stream); cudaEventDestroy(h->snap_ev); }
     cudaFree(h->snap_stage);
     cudaFree(h->q); cudaFree(h->psi); cudaFree(h->f); cudaFree(h->S); cudaFree(h->k0sol);
-    cudaFree(h->scal); cudaFree(h->solve_tmp); cudaFree(h->diag_part);
+    cudaFree(h->scal); cudaFree(h->solve_tmp); cudaFree(h->diag_part); cudaFree(h->ext_part);
     for (cudaEvent_t e : h->evpool) cudaEventDestroy(e);
     for (int a = 0; a < 3; ++a)
         for (int b = 0; b < 3; ++b)
@@ -885,6 +939,32 @@ int qg_diagnostics(qg_handle* h, double* energy, double* enstrophy) {
         energy[m] = out[2 * m];
         enstrophy[m] = out[2 * m + 1];
     }
+    return QG_OK;
+}
+
+int qg_extrema(qg_handle* h, double* out) {
+    if (!h || !out) return QG_ERR_INVALID;
+    if (!h->have_state) return fail(h, QG_ERR_STATE, "qg_extrema: no state uploaded");
+    QG_CUDA(h, cudaSetDevice(h->device));
+    const int nb = h->diag_blocks;
+    if (!h->ext_part) QG_CUDA(h, cudaMalloc((void**)&h->ext_part, ((size_t)h->nm * nb + h->nm) * 8 * sizeof(double)));
+    double* res = h->ext_part + (size_t)h->nm * nb * 8;
+    {
+        KernelTimer t(h, QG_K_DIAG);
+        k5_extrema_partial<<<dim3(nb, h->nm), 256, 0, h->stream>>>(h->field(h->q, h->qcur, 0, 0),
+                                                                   h->field(h->psi, h->pcur, 0, 0), h->g, h->ext_part);
+    }
+    {
+        KernelTimer t(h, QG_K_DIAG);
+        k5_extrema_final<<<h->nm, 256, 0, h->stream>>>(h->ext_part, nb, res);
+    }
+    QG_CUDA(h, cudaGetLastError());
+    if (h->dist_n > 1) QG_CUDA(h, dist_allreduce_max(h, res, 8 * (size_t)h->nm));   // slab extrema -> domain extrema
+    std::vector<double> tmp(8 * (size_t)h->nm);
+    QG_CUDA(h, cudaMemcpyAsync(tmp.data(), res, tmp.size() * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    QG_CUDA(h, cudaStreamSynchronize(h->stream));
+    if (int rc = dist_poll_error(h)) return rc;
+    for (size_t k = 0; k < tmp.size(); ++k) out[k] = (k & 1) ? -tmp[k] : tmp[k];
     return QG_OK;
 }
 

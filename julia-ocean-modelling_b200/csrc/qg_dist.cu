@@ -100,6 +100,10 @@ cudaError_t dist_allreduce_sum(Handle* h, double* buf, size_t count) {
     return nccl_check(h, g_nccl.AllReduce(buf, buf, count, ncclFloat64, ncclSum, (ncclComm_t)h->nccl, h->stream), "AllReduce");
 }
 
+cudaError_t dist_allreduce_max(Handle* h, double* buf, size_t count) {
+    return nccl_check(h, g_nccl.AllReduce(buf, buf, count, ncclFloat64, ncclMax, (ncclComm_t)h->nccl, h->stream), "AllReduce");
+}
+
 // Fill the two ghost rows above and below the local rows of every field of one slot with the
 // neighbours' boundary rows (periodic ring).  Whole padded rows travel, so the x ghosts and the
 // corners arrive with them.

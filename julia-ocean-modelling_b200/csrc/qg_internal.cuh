@@ -146,6 +146,7 @@ cudaError_t dist_halo_exchange(Handle* h, double* base, int slot);   // qg_dist.
 cudaError_t dist_allgather(Handle* h, const double* send, double* recv, size_t count);
 cudaError_t dist_broadcast(Handle* h, double* buf, size_t count, int root);
 cudaError_t dist_allreduce_sum(Handle* h, double* buf, size_t count);
+cudaError_t dist_allreduce_max(Handle* h, double* buf, size_t count);
 void dist_destroy(Handle* h);
 cudaError_t dist_barrier(Handle* h);                       // cross-GPU flag barrier on the handle's stream (peer mode)
 int dist_ipc_export(Handle* h, void* out256);
@@ -210,6 +211,7 @@ struct Handle {
     unsigned long long epoch = 0;    // barrier counter
     bool q_halo_pending = false;     // K1 has pushed q rows to the neighbours and no barrier has run since
     double* diag_part = nullptr;     // partial sums for diagnostics
+    double* ext_part = nullptr;      // partial extrema (qg_extrema)
     int diag_blocks = 0;
     int64_t launches = 0;
     int profiling = 0;

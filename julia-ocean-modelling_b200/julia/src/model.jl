@@ -4,15 +4,14 @@
 # forwarded with `ccall` to libqgb200.so (include/qgb200.h), whose CUDA kernels replace
 # src/schemes/arakawa.jl, src/schemes/laplacian.jl and src/schemes/boundary_conditions.jl.
 #
-# NOTE: there is no Julia toolchain in the build image, so this file is exercised only
-# through its Python twin (julia-ocean-modelling_b200/python/qgb200/model.py), which binds
-# the same symbols with the same argument order.  Keep the two in lock step.
+# NOTE (experimental): there is no Julia toolchain in the build image, so this file has never been
+# executed; the tested binding is its Python twin (julia-ocean-modelling_b200/python/qgb200/model.py),
+# which binds the same symbols with the same argument order.  tests/test_julia_shim.py parses every
+# `ccall` below and checks name, arity and argument types against include/qgb200.h, the field order
+# of QGParams against struct qg_params, and that every type is defined before the `ccall` that names it.
 
 using LinearAlgebra
 using Libdl
-
-include("schemes/laplacian.jl")            # RectangularDomain, get_*_cholesky, sp_solve_* (shims)
-include("host_ic.jl")                       # host-side ghost refresh / Laplacian (initial condition only)
 
 const MINUTES = 60
 const DAY = 60*60*24
@@ -20,6 +19,36 @@ const KM = 1000.0
 const YEAR = 60*60*24*365
 
 const libqgb200 = get(ENV, "QGB200_LIB", joinpath(@__DIR__, "..", "..", "lib", "libqgb200.so"))
+
+# ---- C parameter block (struct qg_params in include/qgb200.h; field order must match) ---------
+# Defined before anything is included: the `ccall` signatures in schemes/laplacian.jl name it.
+struct QGParams
+    M::Int32
+    P::Int32
+    dx::Float64
+    dt::Float64
+    visc::Float64
+    r::Float64
+    U::Float64
+    beta1::Float64
+    beta2::Float64
+    alpha::Float64
+    Pinv::NTuple{4,Float64}   # row-major
+    Pfwd::NTuple{4,Float64}   # row-major
+    H1::Float64
+    H2::Float64
+    S1::Float64
+end
+
+qg_error(h::Ptr{Cvoid}) = unsafe_string(ccall((:qg_last_error, libqgb200), Cstring, (Ptr{Cvoid},), h))
+
+function qg_check(h::Ptr{Cvoid}, rc::Cint)
+    rc == 0 || error("libqgb200 error $rc: $(qg_error(h))")
+    nothing
+end
+
+include("schemes/laplacian.jl")            # RectangularDomain, get_*_cholesky, sp_solve_* (shims)
+include("host_ic.jl")                       # host-side ghost refresh / Laplacian (initial condition only)
 
 struct BaroclinicModel
     H_1::Float64
@@ -60,25 +89,7 @@ beta_1(model::BaroclinicModel) = model.beta + (S1_plus(model) * model.U)
 beta_2(model::BaroclinicModel) = model.beta - (S2_minus(model) * model.U)
 S_eig(model::BaroclinicModel) = -1 / model.R_d^2
 
-# ---- C parameter block (struct qg_params in include/qgb200.h; field order must match) ---------
-struct QGParams
-    M::Int32
-    P::Int32
-    dx::Float64
-    dt::Float64
-    visc::Float64
-    r::Float64
-    U::Float64
-    beta1::Float64
-    beta2::Float64
-    alpha::Float64
-    Pinv::NTuple{4,Float64}   # row-major
-    Pfwd::NTuple{4,Float64}   # row-major
-    H1::Float64
-    H2::Float64
-    S1::Float64
-end
-
+# ---- the parameter block of a model: derived constants by the formulas above ----------------
 function QGParams(model::BaroclinicModel)
     Pinv = P_inv_matrix(model)
     # evolve_psi! of the reference builds P with (H_1, H_1) (src/model.jl:173); reproduced as it runs
@@ -93,13 +104,6 @@ end
 mutable struct QGHandle
     ptr::Ptr{Cvoid}
     model::BaroclinicModel
-end
-
-qg_error(h::Ptr{Cvoid}) = unsafe_string(ccall((:qg_last_error, libqgb200), Cstring, (Ptr{Cvoid},), h))
-
-function qg_check(h::Ptr{Cvoid}, rc::Cint)
-    rc == 0 || error("libqgb200 error $rc: $(qg_error(h))")
-    nothing
 end
 
 const _handles = Dict{BaroclinicModel,QGHandle}()
@@ -130,8 +134,6 @@ qg_step!(h::QGHandle, first_timestep::Integer, nsteps::Integer) = qg_check(h.ptr
     ccall((:qg_step, libqgb200), Cint, (Ptr{Cvoid}, Cint, Cint), h.ptr, first_timestep, nsteps))
 
 # ---- the reference's API --------------------------------------------------------------------------
-"""Initialise the model with a small random psi and then calculate zeta directly
-(reference src/model.jl:37-62; host side, once per run)."""
 """initialise_model on the device (`qg_init_state`): seeded Philox noise instead of the reference's
 unseeded `rand`, same arithmetic (reference src/model.jl:37-62); nothing crosses PCIe."""
 function initialise_model_device!(h, model::BaroclinicModel, seed::Integer)
@@ -140,6 +142,8 @@ function initialise_model_device!(h, model::BaroclinicModel, seed::Integer)
                           h.ptr, UInt64(seed), model.initial_kick * model.U * model.Ly, S1_plus(model), S2_minus(model)))
 end
 
+"""Initialise the model with a small random psi and then calculate zeta directly
+(reference src/model.jl:37-62; host side, once per run)."""
 function initialise_model(model::BaroclinicModel)
     @assert sign(beta_1(model)) == -sign(beta_2(model))
     psi_1 = model.initial_kick * model.U * model.Ly * rand(Float64, (model.M+2, model.P+2))

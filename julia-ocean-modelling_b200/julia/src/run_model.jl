@@ -38,6 +38,23 @@ function log_model_params(model::BaroclinicModel)     # reference src/run_model.
     println("Total steps = ", total_steps, "\n")
 end
 
+# reference src/run_model.jl:41-53 keeps running extrema by scanning host matrices; here the device
+# reduces them (qg_extrema: max q1, min q1, max q2, min q2, max psi1, min psi1, max psi2, min psi2)
+update_max(current_max::Float64, value::Float64) = value > current_max ? value : current_max
+update_min(current_min::Float64, value::Float64) = value < current_min ? value : current_min
+
+function qg_extrema(h)
+    out = zeros(8)
+    qg_check(h.ptr, ccall((:qg_extrema, libqgb200), Cint, (Ptr{Cvoid}, Ptr{Float64}), h.ptr, out))
+    return out
+end
+
+function qg_diagnostics(h)
+    e = zeros(1); z = zeros(1)
+    qg_check(h.ptr, ccall((:qg_diagnostics, libqgb200), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}), h.ptr, e, z))
+    return e[1], z[1]
+end
+
 qg_snapshot_begin!(h, zeta1::Array{Float64, 3}, psi1::Array{Float64, 3}) = qg_check(h.ptr,
     ccall((:qg_snapshot_begin, libqgb200), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}), h.ptr, zeta1, psi1))
 qg_snapshot_end!(h) = qg_check(h.ptr, ccall((:qg_snapshot_end, libqgb200), Cint, (Ptr{Cvoid},), h.ptr))

@@ -10,6 +10,6 @@ from .model import (DAY, KM, MINUTES, YEAR, BaroclinicModel, P_inv_matrix, P_mat
                     close_sessions, evolve_psi, evolve_zeta, get_helmholtz_cholesky, get_poisson_cholesky,
                     initialise_model, make_params, ratio_term, run_model_no_output,
                     sp_solve_modified_helmholtz, sp_solve_poisson, update_doubly_periodic_bc)
-from .runs import (create_metadata, load_restart, load_run, log_model_params, resume_model,  # noqa: F401
-                        run_model, save_restart)
+from .runs import (MONITOR_COLUMNS, create_metadata, load_restart, load_run, log_model_params,  # noqa: F401
+                   resume_model, run_model, save_restart, update_max, update_min)
 from . import slab  # noqa: E402,F401

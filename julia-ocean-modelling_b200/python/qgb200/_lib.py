@@ -51,6 +51,7 @@ SYMBOLS = {
     "qg_step": (C.c_int, [_P, C.c_int, C.c_int]),
     "qg_sync": (C.c_int, [_P]),
     "qg_diagnostics": (C.c_int, [_P, _D, _D]),
+    "qg_extrema": (C.c_int, [_P, _D]),
     "qg_solve": (C.c_int, [_P, C.c_int, _P, _P]),
     "qg_set_profiling": (C.c_int, [_P, C.c_int]),
     "qg_kernel_times": (C.c_int, [_P, _D, C.POINTER(C.c_int64)]),

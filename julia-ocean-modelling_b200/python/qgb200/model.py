@@ -308,6 +308,18 @@ class Session:
             return e[0], z[0]
         return np.array(e[:]), np.array(z[:])
 
+    EXTREMA = ("max_q1", "min_q1", "max_q2", "min_q2", "max_psi1", "min_psi1", "max_psi2", "min_psi2")
+
+    def extrema(self):
+        """Maximum and minimum of q and psi per layer over the interior of the newest level (device
+        reduction; what the reference's update_max / update_min, src/run_model.jl:41-53, compute by
+        scanning a host matrix).  Returns an array of shape (8,) - or (members, 8) - in the order of
+        :attr:`EXTREMA`."""
+        out = (C.c_double * (8 * self.members))()
+        self._ck(self._lib.qg_extrema(self._h, out))
+        a = np.array(out[:]).reshape(self.members, 8)
+        return a[0] if self.members == 1 else a
+
     def solve(self, f, pinned):
         M, P = self.model.M, self.model.P
         f = np.asfortranarray(f, dtype=np.float64)

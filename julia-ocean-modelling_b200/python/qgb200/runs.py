@@ -50,6 +50,19 @@ def log_model_params(model, out=print):
         out(f"{k} = {v}")
 
 
+def update_max(current_max, value):
+    """src/run_model.jl:41-46 (there: the maximum of a host matrix; here the device has reduced it)."""
+    return value if value > current_max else current_max
+
+
+def update_min(current_min, value):
+    """src/run_model.jl:48-53"""
+    return value if value < current_min else current_min
+
+
+MONITOR_COLUMNS = ("timestep", "E", "Z") + Session.EXTREMA
+
+
 def _append(file_name, **arrays):
     """Append ``name -> array`` members to the .npz at `file_name` (created on first use)."""
     with zipfile.ZipFile(file_name, "a", compression=zipfile.ZIP_STORED, allowZip64=True) as zf:
@@ -71,10 +84,17 @@ def _pinned_pair(shape):
 
 
 def run_model(model, file_name, save_results, seed=None, rand_fields=None, device=0, sample_timestep=None,
-              total_steps=None, log=None):
+              total_steps=None, log=None, monitor_every=None, monitor=None):
     """src/run_model.jl:55-93.  Returns ``(zeta, psi)`` like the reference; `seed`,
     `sample_timestep`, `total_steps` override the reference's unseeded RNG / two-day sampling /
-    ``floor(T/dt)`` for tests."""
+    ``floor(T/dt)`` for tests.
+
+    ``monitor_every=n`` adds the diagnostics suite the reference only sketches (its dead
+    update_max / update_min, src/run_model.jl:41-53): at step 0 and every n steps the device reduces
+    energy, enstrophy and the extrema of q and psi (18 doubles cross PCIe per sample).  The time
+    series - columns :data:`MONITOR_COLUMNS` - and the running extrema over the run are stored in
+    the output file as ``monitor`` / ``monitor_running`` and, if a dict is passed as `monitor`,
+    returned in it under the same names."""
     if log is not None:
         log_model_params(model, log)
     if sample_timestep is None:
@@ -90,17 +110,35 @@ def run_model(model, file_name, save_results, seed=None, rand_fields=None, devic
         _append(file_name, zeta_0=zeta[:, :, :, 0], psi_0=psi[:, :, :, 0],
                 metadata=np.frombuffer(json.dumps(create_metadata(model)).encode(), dtype=np.uint8))
     (snap_z, snap_p), _keep = _pinned_pair((model.M + 2, model.P + 2, 2))
+    series, running = [], None
+
+    def sample(s, t):
+        nonlocal running
+        E, Z = s.diagnostics()
+        ex = s.extrema()
+        series.append([float(t), E, Z] + list(ex))
+        if running is None:
+            running = list(ex)
+        else:   # even entries are maxima, odd entries minima
+            running = [update_max(r, v) if k % 2 == 0 else update_min(r, v) for k, (r, v) in enumerate(zip(running, ex))]
+
     with Session(model, 1, device) as s:
         s.upload_initial(zeta, psi)
+        if monitor_every:
+            sample(s, 0)
         t, pending = 0, None
         while t < total_steps:
             nxt = min(total_steps, (t // sample_timestep + 1) * sample_timestep)
+            if monitor_every:
+                nxt = min(nxt, (t // monitor_every + 1) * monitor_every)
             s.step(t + 1, nxt - t)                  # queued behind any snapshot copy still in flight
             if pending is not None:                 # write sample k while the GPU steps towards k+1
                 s.snapshot_end()
                 _append(file_name, **{f"zeta_{pending}": snap_z, f"psi_{pending}": snap_p})
                 pending = None
             t = nxt
+            if monitor_every and t % monitor_every == 0:
+                sample(s, t)
             if save_results and t % sample_timestep == 0:
                 s.snapshot_begin(snap_z, snap_p)
                 pending = t
@@ -108,6 +146,12 @@ def run_model(model, file_name, save_results, seed=None, rand_fields=None, devic
             s.snapshot_end()
             _append(file_name, **{f"zeta_{pending}": snap_z, f"psi_{pending}": snap_p})
         s.download(zeta=zeta, psi=psi)
+    if monitor_every:
+        mon = {"monitor": np.array(series), "monitor_running": np.array(running)}
+        if save_results:
+            _append(file_name, **mon)
+        if monitor is not None:
+            monitor.update(mon)
     return zeta, psi
 
 

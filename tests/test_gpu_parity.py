@@ -407,3 +407,44 @@ def test_two_devices_in_one_process():
         out.append((z, p, f))
     for a, b in zip(*out):
         assert np.array_equal(a, b)
+
+
+def test_run_model_monitor_time_series_and_running_extrema(tmp_path):
+    """the diagnostics suite of run_model - energy / enstrophy time series and the
+    running extrema the reference's dead update_max / update_min (src/run_model.jl:41-53) were
+    meant to keep - against the oracle's trajectory sampled at the same steps; extrema are exact
+    functions of fields that agree to 1e-10."""
+    mo, mg = models(96, 64)
+    fn = str(tmp_path / "run.npz")
+    mon = {}
+    zeta, psi = qgb200.run_model(mg, fn, True, seed=3, sample_timestep=6, total_steps=12, monitor_every=4, monitor=mon)
+    series, running = mon["monitor"], mon["monitor_running"]
+    assert series.shape == (4, 3 + 8) and list(series[:, 0]) == [0, 4, 8, 12]
+    zo, po = o.initialise_model(mo, seed=3)
+    fo = np.zeros_like(zo)
+    fac = o.make_factors(mo, "direct")
+    done, run_ref = 0, None
+    for row in series:
+        t = int(row[0])
+        o.run_steps(mo, zo, po, fo, fac, done + 1, t - done)
+        done = t
+        Eo, Zo = o.diagnostics(mo, zo, po)
+        assert abs(row[1] - Eo) / Eo < 1e-11 and abs(row[2] - Zo) / Zo < 1e-11
+        ex = []
+        for arr in (zo, po):
+            for l in range(2):
+                a = arr[1:-1, 1:-1, l, 0]
+                ex += [a.max(), a.min()]
+        assert np.allclose(row[3:], ex, rtol=1e-10, atol=0.0)
+        run_ref = ex if run_ref is None else [max(r, v) if k % 2 == 0 else min(r, v) for k, (r, v) in enumerate(zip(run_ref, ex))]
+    assert np.allclose(running, run_ref, rtol=1e-10, atol=0.0)
+    with np.load(fn) as z:
+        assert np.array_equal(z["monitor"], series) and np.array_equal(z["monitor_running"], running)
+    assert qgb200.update_max(1.0, 2.0) == 2.0 and qgb200.update_max(3.0, 2.0) == 3.0 and qgb200.update_min(1.0, 2.0) == 1.0
+    # ensembles: one row of extrema per member
+    with qgb200.Session(mg, members=2) as s:
+        s.init_state(5)
+        e = s.extrema()
+        z, p = s.new_state_array(), s.new_state_array()
+        s.download(zeta=z, psi=p)
+    assert e.shape == (2, 8) and e[1, 4] == p[1:-1, 1:-1, 0, 0, 1].max() and e[0, 1] == z[1:-1, 1:-1, 0, 0, 0].min()

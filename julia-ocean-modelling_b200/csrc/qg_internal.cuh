@@ -79,6 +79,9 @@ struct Plan {
     double* coltab;          // [72][ncol] per-column constants of the persistent y-solve (k3_ysolve.cu)
     double2* tw;             // exp(-2 pi i n / M), n < M
     double *rtab, *kap, *rho32, *h32, *rhoL, *hL, *inv1mrP, *pinw, *gw;   // per real column
+    double *logr, *g1mr2;    // ln r and 1 / (1 - r^2) per real column (from the extended-precision r): k3_rank_correct
+    int2* corr_work;         // y-slab mode: (32-column tile, 32-row segment) pairs k3_rank_correct has to touch
+    int ncorr;
     int ngp;                 // gauge partial sums per member (= slabs of the TMA y-solve)
     double k0scale;          // dx^2 / M
 };

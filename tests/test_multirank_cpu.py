@@ -57,6 +57,11 @@ def _worker(rank, world, port, P, e, q):
     As, Be = ym.close_cyclic(gathered, 1.0 / (1.0 - r ** P))   # k3_rank_closure
     cAs, cBe = ym.close_open(items, As[rank], Be[rank])   # chunk level with the ends handed in
     u = ym.apply(g[j0:j1], r, chunks, cAs, cBe)
+    # single-pass variant (k3_ysolve_pipe<3> + k3_rank_correct): solve with zero incoming carries, then add
+    # the carry terms near the slab edges
+    zAs, zBe = ym.close_open(items, 0.0, 0.0)
+    u1 = ym.apply(g[j0:j1], r, chunks, zAs, zBe) + ym.rank_correction(j1 - j0, r, As[rank], Be[rank])
+    assert np.abs(u1 - u).max() <= 1e-13 * np.abs(u).max(), np.abs(u1 - u).max() / np.abs(u).max()
     # slab partition of a reference-layout state array and its reassembly
     full = np.asfortranarray(np.random.default_rng(3).standard_normal((10, P + 2, 2, 3)))
     slab.refresh_global_ghosts(full)
@@ -76,7 +81,7 @@ def _worker(rank, world, port, P, e, q):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("P,e", [(128, 0.2), (256, 6e-4)])
+@pytest.mark.parametrize("P,e", [(128, 0.2), (256, 6e-4), (512, 4.0)])
 def test_two_rank_carry_exchange_matches_global_solve(P, e):
     ctx = mp.get_context("spawn")
     q = ctx.Queue()

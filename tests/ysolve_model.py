@@ -94,6 +94,19 @@ def apply(g, r, chunks, As, Be):
     return u
 
 
+def rank_correction(P, r, a_in, b_in):
+    """What k3_rank_correct adds to a slab solved with ZERO incoming carries (single-pass y-slab mode):
+    -r * (a_in r^(i+1) (1 - r^(2(P-i))) / (1 - r^2) + b_in r^(P-i)), with the kernel's cut-off: rows
+    further than n_cut = 41.6 / -ln r (r^n < 2^-60) from both edges, taken per 32-row segment, are skipped."""
+    i = np.arange(P)
+    lr = np.log(r)
+    d = -r * (a_in * np.exp((i + 1) * lr) * (1.0 - np.exp(2 * (P - i) * lr)) / (1.0 - r * r) + b_in * np.exp((P - i) * lr))
+    ncut = min(P, int(-41.6 / lr) + 1)
+    seg0 = (i // CH) * CH
+    keep = (seg0 < ncut) | (P - (seg0 + CH - 1) <= ncut)
+    return np.where(keep, d, 0.0)
+
+
 def solve_cyclic(g, e):
     r = root(e)
     items, chunks = slab_items(g, r)

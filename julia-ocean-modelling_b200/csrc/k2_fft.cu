@@ -694,6 +694,12 @@ __device__ __forceinline__ void bulk_load(void* dst, const void* src, uint32_t b
                  : "memory");
 }
 
+// One instruction pulls a whole row into L2 ahead of the bulk copy that will fetch it: the ring leaves a
+// copy only about half a row period to land (one buffer of three is in flight while two are worked on).
+__device__ __forceinline__ void bulk_prefetch_l2(const void* src, uint32_t bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
+}
+
 // RowFft16<12>::run with the block barrier replaced by the group's named barrier
 template <int SIGN>
 struct RingFft {
@@ -757,7 +763,7 @@ __device__ __forceinline__ double group_sum(double v, double* sh, int lt, int ba
 }
 
 __global__ void __launch_bounds__(RING_THREADS, 1)
-k2_fft16_ring(const FftArgs a, int rows_per_member, int total_rows) {
+k2_fft16_ring(const FftArgs a, int rows_per_member, int total_rows, int pf) {
     extern __shared__ __align__(128) unsigned char ring_raw[];
     uint64_t* full = reinterpret_cast<uint64_t*>(ring_raw + RING_NBUF * RING_BUF_BYTES);
     constexpr int N = RING_N, TPR = RING_TPR, half = N >> 1;
@@ -775,6 +781,11 @@ k2_fft16_ring(const FftArgs a, int rows_per_member, int total_rows) {
         mbar_expect_tx(fb, (uint32_t)RING_BUF_BYTES);
         bulk_load(dst, a.q1 + member * a.mstride + a.g.at(0, row), N * sizeof(double), fb);
         bulk_load(dst + N * sizeof(double), a.q2 + member * a.mstride + a.g.at(0, row), N * sizeof(double), fb);
+        if (pf && j + pf < nmine) {   // the row `pf` turns of the ring later -> L2
+            const int g2 = blockIdx.x + (j + pf) * G, m2 = g2 / rows_per_member, r2 = g2 - m2 * rows_per_member;
+            bulk_prefetch_l2(a.q1 + m2 * a.mstride + a.g.at(0, r2), N * sizeof(double));
+            bulk_prefetch_l2(a.q2 + m2 * a.mstride + a.g.at(0, r2), N * sizeof(double));
+        }
     };
     if (threadIdx.x == 0) {
         for (int b = 0; b < RING_NBUF; ++b) mbar_init(&full[b], 1);
@@ -813,6 +824,8 @@ k2_fft16_ring(const FftArgs a, int rows_per_member, int total_rows) {
                 }
             }
         }
+        // (the global stores above consumed every value loaded from the buffer, so behind this barrier the loads
+        // have completed, not merely been issued, and the bulk copy may overwrite the buffer)
         group_sync(bar);   // the buffer is free
         if (lt == 0 && j + RING_NBUF < nmine) {
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -881,11 +894,6 @@ k4_fft16_ring(const FftArgs a, int rows_per_member, int total_rows) {
         }
         group_sync(bar);   // the spectral row has been consumed: pass 0 may overwrite it
         fft.template run<false>(v, s, lt, bar);
-        group_sync(bar);   // the last pass has read its inputs: the buffer is free, the results are in registers
-        if (lt == 0 && j + RING_NBUF < nmine) {
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            issue(j + RING_NBUF);
-        }
         double* __restrict__ p1 = a.psi1 + member * a.mstride;
         double* __restrict__ p2 = a.psi2 + member * a.mstride;
         // images of the edge rows: own array (periodic) or the ring neighbours' (NVLink peer memory)
@@ -916,6 +924,14 @@ k4_fft16_ring(const FftArgs a, int rows_per_member, int total_rows) {
                 if (gl) { hi1[o - dyo + M] = o1; hi2[o - dyo + M] = o2; }
                 if (gr_) { hi1[o - dyo - M] = o1; hi2[o - dyo - M] = o2; }
             }
+        }
+        // The stores above depend on every value the last pass loaded from the buffer, and stores do not pass
+        // the barrier: behind it all of the group's shared-memory loads have completed (a barrier alone orders
+        // their issue only) and the bulk copy of row j + 3 may overwrite the buffer.
+        group_sync(bar);
+        if (lt == 0 && j + RING_NBUF < nmine) {
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            issue(j + RING_NBUF);
         }
     }
 }
@@ -1668,18 +1684,20 @@ static cudaError_t launch_pair(Handle* h, const FftArgs& a) {
 
 template <bool FWD>
 static cudaError_t launch_ring(Handle* h, const FftArgs& a) {
-    auto kern = FWD ? k2_fft16_ring : k4_fft16_ring;
     static bool configured_dev[QG_MAX_DEVICES] = {};
     bool& configured = configured_dev[dev_slot(h)];
     if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RING_SMEM);
+        cudaError_t e = FWD ? cudaFuncSetAttribute(k2_fft16_ring, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RING_SMEM)
+                            : cudaFuncSetAttribute(k4_fft16_ring, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RING_SMEM);
         if (e != cudaSuccess) return e;
         configured = true;
     }
     const int total = h->plan.P * h->nm;
     int grid = num_sms();
     if (grid > (total + 1) / 2) grid = (total + 1) / 2;   // both groups of every CTA get a row
-    kern<<<grid, RING_THREADS, RING_SMEM, h->stream>>>(a, h->plan.P, total);
+    static const int pf = getenv("QG_RING_PF") ? atoi(getenv("QG_RING_PF")) : 3;
+    if (FWD) k2_fft16_ring<<<grid, RING_THREADS, RING_SMEM, h->stream>>>(a, h->plan.P, total, pf);
+    else k4_fft16_ring<<<grid, RING_THREADS, RING_SMEM, h->stream>>>(a, h->plan.P, total);
     return cudaGetLastError();
 }
 

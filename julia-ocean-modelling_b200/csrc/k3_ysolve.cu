@@ -786,8 +786,6 @@ k3_ysolve_pipe(const __grid_constant__ CUtensorMap tmS, const __grid_constant__ 
         double v[32];
 #pragma unroll
         for (int i = 0; i < 32; ++i) v[i] = live ? t[i * TS_WC] : 0.0;
-        __syncthreads();   // the tile is in registers: the buffer is free for the next slab
-        if (tid == 0 && w + ncluster < nwork) issue(w + ncluster, par ^ 1);
         K3_ACC(2);
 
         const double r = ct[CT_R * TS_WC + l];
@@ -829,6 +827,16 @@ k3_ysolve_pipe(const __grid_constant__ CUtensorMap tmS, const __grid_constant__ 
             }
         }
         __syncthreads();
+        // The tile is in registers AND every load of it has delivered its value: the stores of F and G above
+        // depend on all 32 of them, and a store cannot pass the barrier.  Only now may the next slab's TMA copies
+        // overwrite the buffer.  (Round 1 issued them right behind a barrier that directly followed the 32 loads:
+        // a barrier orders the loads' ISSUE, not their completion, and the TMA engine does not go through the
+        // load/store pipe that keeps generic accesses in order - about one run in ten of 43 steps at 4096^2 then
+        // differed in the last bits, scripts/determinism.py; the per-slab first-generation kernel never did.)
+        if (tid == 0 && w + ncluster < nwork) {
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            issue(w + ncluster, par ^ 1);
+        }
         K3_ACC(3);
 
         // ---- carries: warp-level cyclic reduction per column pair, one push-based exchange ----------

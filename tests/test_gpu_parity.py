@@ -476,3 +476,25 @@ def test_run_model_monitor_time_series_and_running_extrema(tmp_path):
         z, p = s.new_state_array(), s.new_state_array()
         s.download(zeta=z, psi=p)
     assert e.shape == (2, 8) and e[1, 4] == p[1:-1, 1:-1, 0, 0, 1].max() and e[0, 1] == z[1:-1, 1:-1, 0, 0, 0].min()
+
+
+def test_repeated_runs_are_bit_identical_4096():
+    """The same run repeated on one handle gives bit-identical fields.  Guards the tile-reuse race found
+    in round 2 (k3_ysolve_pipe issued the next slab's TMA copies behind a barrier that directly followed
+    the 32 shared-memory loads of the current tile: the barrier orders the loads' issue, not their
+    completion, and about one 43-step run in ten at 4096 x 4096 came out different in the last bits;
+    profiles/r02/determinism_k3_tile_race.log).  Every kernel of the step is deterministic by
+    construction (fixed-order reductions), so any difference is a race."""
+    import hashlib
+    mo, mg = models(4096, 4096, dt=300.0)
+    seen = set()
+    with qgb200.Session(mg) as s:
+        z1 = np.zeros((4098, 4098, 2), order="F")
+        p1 = np.zeros((4098, 4098, 2), order="F")
+        for rep in range(8):
+            s.init_state(3)
+            s.step(1, 40)
+            s.snapshot_begin(z1, p1)
+            s.snapshot_end()
+            seen.add(hashlib.sha256(z1.tobytes() + p1.tobytes()).hexdigest())
+    assert len(seen) == 1, f"{len(seen)} different results in 8 identical runs"

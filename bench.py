@@ -361,23 +361,32 @@ def slab_parity_leg(torch, dist, qgb200, np, stream, local_rank, rank, world, st
     j0 = rank * pl_rows
     refh = ref.cpu().numpy()   # [2][layer][P+2][M+2]
     rel = lambda x, y: float(np.abs(x - y).max() / np.abs(y).max())
-    errs = []
+    errs, where = [], []
     for k, mine in ((0, zl), (1, pl)):
         want = refh[k][:, j0:j0 + pl_rows + 2, :]                        # ghost-inclusive rows of this slab
         got = np.ascontiguousarray(mine[:, :, :, 0].T)                    # [layer][P_loc+2][M+2]
         errs.append(max(rel(got[l], want[l]) for l in range(2)))
+        d = np.abs(got - want)
+        l, jj, ii = np.unravel_index(int(np.argmax(d)), d.shape)
+        where.append({"rank": rank, "layer": int(l), "local_row": int(jj) - 1, "col": int(ii) - 1,
+                      "interior_only": max(rel(got[x][1:-1, 1:-1], want[x][1:-1, 1:-1]) for x in range(2))})
     Eo, Zo = float(ez[0]), float(ez[1])
     errs += [abs(E - Eo) / abs(Eo), abs(Z - Zo) / abs(Zo)]
-    allerrs = [None] * world
+    allerrs, allwhere = [None] * world, [None] * world
     dist.all_gather_object(allerrs, errs)
+    dist.all_gather_object(allwhere, where)
     worst = np.max(np.array(allerrs, dtype=np.float64), axis=0)
+    worst_rank = int(np.argmax(np.array(allerrs, dtype=np.float64)[:, 1]))
     ok = bool(worst[0] <= 1e-10 and worst[1] <= 1e-10 and worst[2] <= 1e-8 and worst[3] <= 1e-8)
     return {"grid": [M, P], "steps": steps, "ranks": world, "q": float(worst[0]), "psi": float(worst[1]),
             "E": float(worst[2]), "Z": float(worst[3]), "ok": ok,
             "tolerance": "q, psi <= 1e-10 relative (max norm, per layer, ghost rows included), E, Z <= 1e-8",
             "against": f"oracle/qg_oracle.c on the global grid from the same device-drawn initial condition "
                        f"({t_oracle:.1f} s on the host)",
-            "exchange": "NVLink peer stores + flag barriers" if peer else "NCCL"}
+            "exchange": "NVLink peer stores + flag barriers" if peer else "NCCL",
+            "worst_cell": {"q": allwhere[int(np.argmax(np.array(allerrs, dtype=np.float64)[:, 0]))][0],
+                           "psi": allwhere[worst_rank][1]},
+            "per_rank": [[float(x) for x in e[:2]] for e in allerrs]}
 
 
 def slab_timed_leg(torch, dist, qgb200, np, stream, local_rank, rank, world, M, P, W, K):

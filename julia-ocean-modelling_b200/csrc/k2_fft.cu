@@ -50,12 +50,23 @@ __device__ __forceinline__ double2 twid(const double2* __restrict__ tw, int idx)
 
 // Q1[0] of one row: the compact k=0 Poisson column.  In y-slab peer mode the value goes straight
 // into every rank's gathered column (NVLink peer stores) instead of a local copy + all-gather.
-__device__ __forceinline__ void store_col0(const FftArgs& a, int member, int row, double v) {
+// `pushed` is set when peer stores were issued: the calling kernel ends with peer_store_fence(pushed).
+__device__ __forceinline__ void store_col0(const FftArgs& a, int member, int row, double v, bool& pushed) {
     if (a.col0_n > 0) {
         for (int r = 0; r < a.col0_n; ++r) a.col0_peer[r][a.col0_off + row] = v;
+        pushed = true;
     } else {
         a.col0[(int64_t)member * a.pl.P + row] = v;
     }
+}
+
+// Peer stores are posted writes over NVLink.  The thread that issued them waits for their acknowledgement
+// (one system-scope fence, which covers all its earlier stores) before it exits, so that the flag barrier
+// enqueued behind the kernel can never overtake them: the barrier kernel's own fence orders only its own
+// thread's writes.  Without this an 8-rank run of 2048 x 4096 departed from the oracle by 7e-6 (stale halo rows
+// at the ring's seam), profiles/r02/slab_r02s_n8.log -> slab_r02u_n8.log.
+__device__ __forceinline__ void peer_store_fence(bool pushed) {
+    if (pushed) __threadfence_system();
 }
 
 // bank-conflict-free placement of complex slot i (16-byte elements)
@@ -269,6 +280,7 @@ k2_fft_forward(const FftArgs a, int ngroups_per_member, int ngroups_total) {
     F fft;
     fft.init(a.pl.tw, lt);
     const double A0 = a.A[0], A1 = a.A[1], A2 = a.A[2], A3 = a.A[3];
+    bool pushed = false;   // this thread stored into other ranks' memory (y-slab peer mode)
 
     for (int grp = blockIdx.x; grp < ngroups_total; grp += gridDim.x) {
         const int member = grp / ngroups_per_member;
@@ -298,7 +310,7 @@ k2_fft_forward(const FftArgs a, int ngroups_per_member, int ngroups_total) {
                     const double2 z0 = s[swz(0)];
                     out[0] = z0;
                     out[half] = s[swz(half)];
-                    store_col0(a, member, row, z0.x);   // Q1[0]: the Poisson k=0 column
+                    store_col0(a, member, row, z0.x, pushed);   // Q1[0]: the Poisson k=0 column
                 } else {
                     const double2 X = s[swz(k)], Y = s[swz(N - k)];
                     out[k] = make_double2(0.5 * (X.x + Y.x), 0.5 * (X.y - Y.y));        // Q1[k]
@@ -308,6 +320,7 @@ k2_fft_forward(const FftArgs a, int ngroups_per_member, int ngroups_total) {
         }
         __syncthreads();   // the row buffer is reused by the next group
     }
+    peer_store_fence(pushed);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -390,6 +403,7 @@ k4_fft_inverse(const FftArgs a, int ngroups_per_member, int ngroups_total) {
                     if (gr) { hi1[o - dyo - M] = o1; hi2[o - dyo - M] = o2; }
                 }
             }
+            if ((gb | gt) && !a.periodic_y) __threadfence_system();   // peer stores acknowledged before the thread moves on
         }
         __syncthreads();
     }
@@ -523,6 +537,7 @@ k2_fft16_forward(const FftArgs a, int ngroups_per_member, int ngroups_total, int
     F fft;
     fft.init(a.pl.tw, lt);
     const double A0 = a.A[0], A1 = a.A[1], A2 = a.A[2], A3 = a.A[3];
+    bool pushed = false;   // this thread stored into other ranks' memory (y-slab peer mode)
 
     for (int grp = blockIdx.x; grp < ngroups_total; grp += gridDim.x) {
         const int member = grp / ngroups_per_member;
@@ -564,7 +579,7 @@ k2_fft16_forward(const FftArgs a, int ngroups_per_member, int ngroups_total, int
                     const double2 z0 = s[swz16(0)];
                     out[0] = z0;
                     out[half] = s[swz16(half)];
-                    store_col0(a, member, row, z0.x);   // Q1[0]: the Poisson k=0 column
+                    store_col0(a, member, row, z0.x, pushed);   // Q1[0]: the Poisson k=0 column
                 } else {
                     const double2 X = s[swz16(k)], Y = s[swz16(N - k)];
                     out[k] = make_double2(0.5 * (X.x + Y.x), 0.5 * (X.y - Y.y));        // Q1[k]
@@ -574,6 +589,7 @@ k2_fft16_forward(const FftArgs a, int ngroups_per_member, int ngroups_total, int
         }
         __syncthreads();   // the row buffer is reused by the next group
     }
+    peer_store_fence(pushed);
 }
 
 template <int LOG2N>
@@ -657,6 +673,7 @@ k4_fft16_inverse(const FftArgs a, int ngroups_per_member, int ngroups_total, int
                     if (gr) { hi1[o - dyo - M] = o1; hi2[o - dyo - M] = o2; }
                 }
             }
+            if ((gb | gt) && !a.periodic_y) __threadfence_system();   // peer stores acknowledged before the thread moves on
         }
         __syncthreads();
     }
@@ -771,6 +788,7 @@ k2_fft16_ring(const FftArgs a, int rows_per_member, int total_rows, int pf) {
     RingFft<-1> fft;
     fft.init(a.pl.tw, lt);
     const double A0 = a.A[0], A1 = a.A[1], A2 = a.A[2], A3 = a.A[3];
+    bool pushed = false;   // this thread stored into other ranks' memory (y-slab peer mode)
     const int G = gridDim.x;
     const int nmine = (total_rows - (int)blockIdx.x + G - 1) / G;   // this CTA's rows: blockIdx.x + j * G
 
@@ -816,7 +834,7 @@ k2_fft16_ring(const FftArgs a, int rows_per_member, int total_rows, int pf) {
                     const double2 z0 = s[swz16(0)];
                     out[0] = z0;
                     out[half] = s[swz16(half)];
-                    store_col0(a, member, row, z0.x);   // Q1[0]: the Poisson k=0 column
+                    store_col0(a, member, row, z0.x, pushed);   // Q1[0]: the Poisson k=0 column
                 } else {
                     const double2 X = s[swz16(k)], Y = s[swz16(N - k)];
                     out[k] = make_double2(0.5 * (X.x + Y.x), 0.5 * (X.y - Y.y));        // Q1[k]
@@ -832,6 +850,7 @@ k2_fft16_ring(const FftArgs a, int rows_per_member, int total_rows, int pf) {
             issue(j + RING_NBUF);
         }
     }
+    peer_store_fence(pushed);
 }
 
 __global__ void __launch_bounds__(RING_THREADS, 1)
@@ -925,6 +944,7 @@ k4_fft16_ring(const FftArgs a, int rows_per_member, int total_rows) {
                 if (gr_) { hi1[o - dyo - M] = o1; hi2[o - dyo - M] = o2; }
             }
         }
+        if ((gb | gt) && !a.periodic_y) __threadfence_system();   // peer stores acknowledged before the buffer hand-over
         // The stores above depend on every value the last pass loaded from the buffer, and stores do not pass
         // the barrier: behind it all of the group's shared-memory loads have completed (a barrier alone orders
         // their issue only) and the bulk copy of row j + 3 may overwrite the buffer.
@@ -974,6 +994,7 @@ k2_rfft_forward(const FftArgs a, int ngroups_per_member, int ngroups_total, int 
     F fft;
     fft.init(a.pl.tw, lt, 2, fft_smem + N);   // half-length twiddles: exp(-2 pi i n / N) = tw[2n]
     const double2 w0 = __ldg(a.pl.tw + lt);   // W^lt, W = exp(-2 pi i / M)
+    bool pushed = false;   // this thread stored into other ranks' memory (y-slab peer mode)
 
     for (int grp = blockIdx.x; grp < ngroups_total; grp += gridDim.x) {
         const int member = grp / ngroups_per_member;
@@ -1010,7 +1031,7 @@ k2_rfft_forward(const FftArgs a, int ngroups_per_member, int ngroups_total, int 
                 outs[2 * N + field] = Z0.x - Z0.y;          // X[N]  -> slot M/2
                 const double2 Xh = cconj(Zh);               // X[N/2]
                 if (field == 0) out[N / 2] = Xh; else out[M - N / 2] = Xh;
-                if (field == 0) store_col0(a, member, row, Z0.x + Z0.y);
+                if (field == 0) store_col0(a, member, row, Z0.x + Z0.y, pushed);
             } else {
                 const double2 Za = s[swz(k)], Zb = s[swz(N - k)];
                 const double2 E = make_double2(0.5 * (Za.x + Zb.x), 0.5 * (Za.y - Zb.y));
@@ -1023,6 +1044,7 @@ k2_rfft_forward(const FftArgs a, int ngroups_per_member, int ngroups_total, int 
         }
         __syncthreads();
     }
+    peer_store_fence(pushed);
 }
 
 template <int LOG2N>
@@ -1118,6 +1140,7 @@ k4_rfft_inverse(const FftArgs a, int ngroups_per_member, int ngroups_total, int 
                 if (gr) *reinterpret_cast<double2*>(phi + o - dyo - M) = z;
             }
         }
+        if ((gb | gt) && !a.periodic_y) __threadfence_system();   // peer stores acknowledged
         __syncthreads();
     }
 }
@@ -1240,6 +1263,7 @@ __device__ __forceinline__ void pair_forward_body(const FftArgs& a, int units_pe
     const double2 wn = __ldg(a.pl.tw + 2 * lt);             // W_N^lt
     const double2 wdif = c ? make_double2(wn.y, -wn.x) : wn;   // W_N^(lt + c H/2) = (-i)^c W_N^lt
     const double2 wsp = __ldg(a.pl.tw + 2 * lt + c);        // W_M^(2 lt + c)
+    bool pushed = false;   // this thread stored into other ranks' memory (y-slab peer mode)
     __syncthreads();
     cluster_sync_all();   // both CTAs' mbarriers exist before anybody sends
 
@@ -1301,7 +1325,7 @@ __device__ __forceinline__ void pair_forward_body(const FftArgs& a, int units_pe
                 outs[2 * N + field] = Z0.x - Z0.y;          // X[N]  -> slot M/2
                 const double2 Xh = cconj(Zh);               // X[N/2]
                 if (field == 0) out[N / 2] = Xh; else out[M - N / 2] = Xh;
-                if (field == 0) store_col0(a, member, row, Z0.x + Z0.y);
+                if (field == 0) store_col0(a, member, row, Z0.x + Z0.y, pushed);
             } else {
                 const double2 Za = s[swz16(k)], Zb = s[swz16(H - k - (int)c)];
                 const double2 E = make_double2(0.5 * (Za.x + Zb.x), 0.5 * (Za.y - Zb.y));
@@ -1314,6 +1338,7 @@ __device__ __forceinline__ void pair_forward_body(const FftArgs& a, int units_pe
         }
         __syncthreads();   // the row buffer is reused by the next unit
     }
+    peer_store_fence(pushed);
     cluster_sync_all();   // nobody leaves while the partner may still write to it
 }
 
@@ -1436,6 +1461,7 @@ __device__ __forceinline__ void pair_inverse_body(const FftArgs& a, int units_pe
                 }
             }
         }
+        if ((gb | gt) && !a.periodic_y) __threadfence_system();   // peer stores acknowledged
         // no block barrier needed here: the next unit's pre-processing writes the buffer, whose last
         // readers (the pass-2 loads) are separated from it by the barriers inside run()
     }
@@ -1459,6 +1485,7 @@ k2_dft_forward(const FftArgs a) {
     const int N = a.pl.M, row = blockIdx.x, member = blockIdx.y;
     double2* z = fft_smem;
     double2* Z = fft_smem + N;
+    bool pushed = false;   // this thread stored into other ranks' memory (y-slab peer mode)
     const double* __restrict__ q1 = a.q1 + member * a.mstride + a.g.at(0, row);
     const double* __restrict__ q2 = a.q2 + member * a.mstride + a.g.at(0, row);
     for (int n = threadIdx.x; n < N; n += blockDim.x) {
@@ -1481,13 +1508,14 @@ k2_dft_forward(const FftArgs a) {
     for (int k = threadIdx.x; k <= N / 2; k += blockDim.x) {
         if (k == 0 || 2 * k == N) {
             out[k] = Z[k];
-            if (k == 0) store_col0(a, member, row, Z[0].x);
+            if (k == 0) store_col0(a, member, row, Z[0].x, pushed);
         } else {
             const double2 A = Z[k], B = Z[N - k];
             out[k] = make_double2(0.5 * (A.x + B.x), 0.5 * (A.y - B.y));
             out[N - k] = make_double2(0.5 * (A.y + B.y), 0.5 * (B.x - A.x));
         }
     }
+    peer_store_fence(pushed);
 }
 
 __global__ void __launch_bounds__(256)
@@ -1550,6 +1578,7 @@ k4_dft_inverse(const FftArgs a) {
             if (gr) { hi1[o - dyo - M] = o1; hi2[o - dyo - M] = o2; }
         }
     }
+    if ((gb | gt) && !a.periodic_y) __threadfence_system();   // peer stores acknowledged
 }
 
 // ---------------------------------------------------------------------------------------

@@ -125,6 +125,7 @@ __global__ void __launch_bounds__(256) k3_gauge(const YArgs a) {
         if ((M & 1) == 0) t += row0[M];
         a.scal[member * 4 + 1] = t;
         for (int r = 0; r < a.peer_n; ++r) a.scal_peer[r][member * 4 + 1] = t;   // y-slab peer mode: every rank's copy
+        if (a.peer_n > 0) __threadfence_system();   // posted NVLink writes acknowledged before the kernel ends
     }
 }
 
@@ -763,6 +764,7 @@ k3_ysolve_pipe(const __grid_constant__ CUtensorMap tmS, const __grid_constant__ 
     long long acc[8] = {0, 0, 0, 0, 0, 0, 0, 0}, last = clock64();
 #endif
     uint32_t it = 0;
+    bool pushed = false;   // this lane stored rank-level aggregates into other ranks' memory (y-slab peer mode)
     for (int w = cid; w < nwork + nmember; w += ncluster, ++it) {
         if (w >= nwork) {   // block-uniform
             if (cr == 0) k0_column_solve(a, w - nwork, red_sh);
@@ -926,6 +928,7 @@ k3_ysolve_pipe(const __grid_constant__ CUtensorMap tmS, const __grid_constant__ 
                     dst[ncol] = Rt;
                     dst[2 * ncol] = Xr;
                     dst[3 * ncol] = Yr;
+                    pushed = true;
                 }
                 if (MODE == 1) continue;   // warp-uniform; sF / sG are rewritten only after the next iteration's barrier
             }
@@ -1009,6 +1012,9 @@ k3_ysolve_pipe(const __grid_constant__ CUtensorMap tmS, const __grid_constant__ 
     if (tid == 0 && g_k3_trace)
         for (int i = 0; i < 8; ++i) g_k3_trace[(size_t)blockIdx.x * 8 + i] = acc[i];
 #endif
+    // posted NVLink writes: acknowledged before the lane exits, so that the flag barrier enqueued behind this
+    // kernel cannot overtake them (one system-scope fence covers all the lane's earlier stores; see k2_fft.cu)
+    if (pushed) __threadfence_system();
     cluster.sync();   // no CTA leaves while a peer may still push to it or read its aggregates
 }
 

@@ -799,6 +799,9 @@ int qg_init_state(qg_handle* h, uint64_t seed, double amplitude, double S1, doub
                                               row0, h->Pglob);
     }
     QG_CUDA(h, cudaGetLastError());
+    // y-slab peer mode: no rank may start stepping (and storing edge rows into its neighbours' arrays) before
+    // every rank's memsets above have run
+    if (h->peer_ok) QG_CUDA(h, dist_barrier(h));
     h->have_state = true;
     return QG_OK;
 }

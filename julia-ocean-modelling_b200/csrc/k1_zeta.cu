@@ -94,7 +94,6 @@ k1_zeta_step(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ C
 
     double* __restrict__ fn = a.fn + foff;
     double* __restrict__ qn = a.qn + foff;
-    bool pushed = false;   // this thread stored into a ring neighbour's memory (y-slab peer mode)
     const double beta = a.beta[layer];
     const int sx = lx + GHOST;   // column in the psi tile
     const int qx = lx + GHOST;   // column in the q tile
@@ -150,7 +149,6 @@ k1_zeta_step(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ C
         if (gl) qn[o + a.g.M] = qnew;
         if (gr) qn[o - a.g.M] = qnew;
         if (gb | gt) {   // own array (periodic in y) or the ring neighbour's, over NVLink (y-slab mode)
-            pushed = true;
             const int64_t dyo = (int64_t)a.g.P * a.g.pitch;
             if (gb) {
                 double* __restrict__ im = a.qimg_lo + foff;
@@ -164,16 +162,17 @@ k1_zeta_step(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ C
                 if (gl) im[o - dyo + a.g.M] = qnew;
                 if (gr) im[o - dyo - a.g.M] = qnew;
             }
+            // y-slab peer mode: these were posted writes over NVLink.  The thread waits for their acknowledgement
+            // (at most twice: it owns at most two edge rows), so that the flag barrier enqueued behind this kernel
+            // can never overtake them - the barrier kernel's own fence covers only its own thread's writes.  (Placed
+            // here and not behind the loop: code behind the loop costs the main path 7 registers.)
+            if (!a.periodic_y) __threadfence_system();
         }
         // roll the windows
         p_sw = p_w; p_s = p_c; p_se = p_e; p_w = p_nw; p_c = p_n; p_e = p_ne;
         q_sw = q_w; q_s = q_c; q_se = q_e; q_w = q_nw; q_c = q_n; q_e = q_ne;
         l_s = l_c; l_c = l_n;
     }
-    // Peer stores are posted writes over NVLink: the thread that issued them waits for their acknowledgement
-    // before it exits, so that the flag barrier enqueued behind this kernel can never overtake them (its own
-    // fence covers only the barrier kernel's thread).
-    if (pushed && !a.periodic_y) __threadfence_system();
 }
 
 template <int TY>

@@ -103,7 +103,10 @@ int qg_upload_initial_state(qg_handle* h, const double* zeta, const double* psi)
  * (:47-48) in level 1; history levels and f_store zero.  The reference draws from Julia's
  * unseeded global RNG; here the stream is Philox4x32-10 with counter (j*M + i, member*2 + layer)
  * and key `seed`, so a run is reproducible from (seed, parameters) alone.  S1, S2 are
- * S1_plus / S2_minus of src/model.jl:113-115, evaluated by the host shim. */
+ * S1_plus / S2_minus of src/model.jl:113-115, evaluated by the host shim.  On a y-slab handle
+ * (qg_dist_init) j is the GLOBAL row index: every rank draws exactly its rows of the single-GPU
+ * field, its neighbours' rows into the ghost rows included, without any exchange (collective
+ * only in that all ranks must call it, and in peer mode it ends with a flag barrier). */
 int qg_init_state(qg_handle* h, uint64_t seed, double amplitude, double S1, double S2);
 
 /* Device -> host, all three time levels, ghosts included, reference layout.  Any pointer

@@ -59,7 +59,15 @@ qg_snapshot_begin!(h, zeta1::Array{Float64, 3}, psi1::Array{Float64, 3}) = qg_ch
     ccall((:qg_snapshot_begin, libqgb200), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}), h.ptr, zeta1, psi1))
 qg_snapshot_end!(h) = qg_check(h.ptr, ccall((:qg_snapshot_end, libqgb200), Cint, (Ptr{Cvoid},), h.ptr))
 
-function run_model(model::BaroclinicModel, file_name::String, save_results::Bool)
+"""Columns of the `monitor` time series written by `run_model(...; monitor_every = n)`."""
+const MONITOR_COLUMNS = ("timestep", "E", "Z", "max_q1", "min_q1", "max_q2", "min_q2",
+                         "max_psi1", "min_psi1", "max_psi2", "min_psi2")
+
+# `monitor_every = n` (0 = off, the reference's behaviour) samples energy, enstrophy and the extrema of q and
+# psi on the device at step 0 and every n steps, keeps the running extrema with update_max / update_min
+# (the reference defines both, src/run_model.jl:41-53, and never calls them) and writes "monitor" (one row
+# per sample) and "monitor_running" (8 values) into the output file.
+function run_model(model::BaroclinicModel, file_name::String, save_results::Bool; monitor_every::Int=0)
     log_model_params(model)
 
     sample_interval = 1.0*DAY
@@ -84,6 +92,21 @@ function run_model(model::BaroclinicModel, file_name::String, save_results::Bool
                           h.ptr, zeta, psi))
     snap_zeta = zeros(model.M+2, model.P+2, 2)
     snap_psi = zeros(model.M+2, model.P+2, 2)
+    series = Vector{Vector{Float64}}()
+    running = Float64[]
+    function sample!(t::Int)
+        e, z = qg_diagnostics(h)
+        ex = qg_extrema(h)
+        push!(series, vcat(Float64[t, e, z], ex))
+        if isempty(running)
+            running = copy(ex)
+        else
+            for k in 1:8      # odd entries are maxima, even entries minima
+                running[k] = isodd(k) ? update_max(running[k], ex[k]) : update_min(running[k], ex[k])
+            end
+        end
+    end
+    monitor_every > 0 && sample!(0)
 
     println("Running simulation... \n")
     t = 0
@@ -91,6 +114,9 @@ function run_model(model::BaroclinicModel, file_name::String, save_results::Bool
     bar = ProgressBar(total=total_steps)
     while t < total_steps
         nxt = min(total_steps, (div(t, sample_timestep) + 1) * sample_timestep)
+        if monitor_every > 0
+            nxt = min(nxt, (div(t, monitor_every) + 1) * monitor_every)
+        end
         qg_step!(h, t + 1, nxt - t)              # queued behind the snapshot copy, if any
         if pending > 0                            # write sample k while the GPU steps towards k+1
             qg_snapshot_end!(h)
@@ -102,6 +128,9 @@ function run_model(model::BaroclinicModel, file_name::String, save_results::Bool
         end
         update(bar, nxt - t)
         t = nxt
+        if monitor_every > 0 && t % monitor_every == 0
+            sample!(t)
+        end
         if save_results && t % sample_timestep == 0
             qg_snapshot_begin!(h, snap_zeta, snap_psi)
             pending = t
@@ -115,6 +144,12 @@ function run_model(model::BaroclinicModel, file_name::String, save_results::Bool
         end
     end
     qg_download!(h, zeta, psi, nothing)
+    if monitor_every > 0 && save_results
+        jldopen(file_name, "r+") do file
+            write(file, "monitor", permutedims(hcat(series...)))
+            write(file, "monitor_running", running)
+        end
+    end
 
     return zeta, psi
 end

@@ -199,3 +199,23 @@ def test_persistent_ysolve_algebra_matches_dense_cyclic_solve():
     for i in range(31, -1, -1):
         acc = y[i] + r * acc; zz[i] = acc
     assert np.allclose(z + Ac * cA + Bc * cB, zz, rtol=1e-13, atol=1e-13)
+
+
+def test_bench_reference_arm_prints_the_contract_line():
+    """bench.py --impl reference: the reference algorithm on the host cores, honouring --steps / --warmup, with the
+    same `config` dictionary the GPU arm prints for that grid and GPU count, `impl`, `cpu_baseline` and a zero-copy `e2e`."""
+    import json
+    import subprocess
+    import sys
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--grid", "64", "64",
+                          "--steps", "3", "--warmup", "2", "--gpus", "2"], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = json.loads([l for l in out.stdout.splitlines() if l.startswith("{")][-1])
+    sys.path.insert(0, ROOT)
+    import bench
+    assert line["impl"] == "reference" and line["steps"] == 3 and line["warmup"] == 2 and line["n_gpus"] == 2
+    assert line["config"] == bench.workload_config(64, 64, 2, 1, bench.model_args(64, 64)["dt"])
+    assert line["metric"] == bench.METRIC and line["unit"] == bench.UNIT and line["higher_is_better"] is True
+    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["value"] == line["value"]
+    assert line["e2e"] == {"value": line["value"], "unit": bench.UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert line["gpu_launches"] == 0

@@ -49,9 +49,11 @@ def main():
     ap.add_argument("--out", default=None)
     ap.add_argument("--samples", type=int, default=20)
     ap.add_argument("--reference-columns", action="store_true")
+    ap.add_argument("--reference-only", action="store_true",
+                    help="only the B1 reference-algorithm columns (runs without a GPU)")
     args = ap.parse_args()
     o = None
-    if args.reference_columns:
+    if args.reference_columns or args.reference_only:
         sys.path.insert(0, os.path.join(ROOT, "oracle"))
         import qg_oracle as o
     Ms = list(range(8, 129, 8)) if args.parts else [8, 16, 32, 64, 128]
@@ -61,10 +63,13 @@ def main():
         m = model(M, dt)
         r = (np.asfortranarray(np.random.default_rng(1).random((M + 2, M + 2))),
              np.asfortranarray(np.random.default_rng(2).random((M + 2, M + 2))))
-        qgb200.run_model_no_output(m, rand_fields=r)   # warm-up (library load, plan caches)
-        total = best(lambda: qgb200.run_model_no_output(m, rand_fields=r), args.samples)
-        row = {"M": M, "total_time" if args.parts else "Time": total}
-        if args.parts:
+        total = None
+        row = {"M": M}
+        if not args.reference_only:
+            qgb200.run_model_no_output(m, rand_fields=r)   # warm-up (library load, plan caches)
+            total = best(lambda: qgb200.run_model_no_output(m, rand_fields=r), args.samples)
+            row["total_time" if args.parts else "Time"] = total
+        if args.parts and not args.reference_only:
             zeta, psi = qgb200.initialise_model(m, rand_fields=r)
             f = np.zeros_like(zeta)
             with qgb200.Session(m) as s:
@@ -97,7 +102,8 @@ def main():
             o.run_steps(mo, zo, po, fo, fac, 1, steps)
             row["ref_loop_time"] = time.perf_counter() - t0
             row["ref_cell_steps_per_s"] = M * M * steps / row["ref_loop_time"]
-            row["gpu_speedup_whole_run"] = row["ref_total_time" if args.parts else "ref_Time"] / total
+            if total is not None:
+                row["gpu_speedup_whole_run"] = row["ref_total_time" if args.parts else "ref_Time"] / total
             if args.parts:
                 row["ref_psi_time"] = best(lambda: o.evolve_psi(mo, zo, po, *fac), 3)
                 row["ref_zeta_time"] = best(lambda: o.evolve_zeta(mo, zo, po, 1, fo), 3)

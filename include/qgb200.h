@@ -207,6 +207,16 @@ int qg_dist_ipc_export(qg_handle* h, void* out256);
 int qg_dist_ipc_import(qg_handle* h, const void* all_ranks);
 int qg_dist_ipc_blobs_share_device(const void* all_ranks, int nranks);
 
+/* Host-side view of the spectral plan, computed without a GPU (inspection and tests; the handle builds its
+ * plan with the same routines).  For every real column c < 2M of the packed spectral layout: r[c], the decay
+ * per row of the y-recurrences (0 for the singular Poisson k = 0 column), and kappa[c] = -r dx^2 / M, the scale
+ * that turns the second sweep into the solution.  With worklist_len != NULL also the (32-column tile, 32-row
+ * segment) pairs the y-slab edge correction touches for a slab of `rows_local` rows (a multiple of 32):
+ * worklist[2i], worklist[2i+1], at most worklist_capacity pairs are written, *worklist_len is the full count.
+ * Any output pointer may be NULL. */
+int qg_plan_probe(const qg_params* params, int rows_local, double* r, double* kappa, int32_t* worklist,
+                  int worklist_capacity, int* worklist_len);
+
 /* Raw device pointers for zero-copy interop (multi-GPU plumbing, torch tensors):
  * which = 0: q, 1: psi, 2: f_store, 3: spectral scratch.  Returns the base pointer, the
  * row pitch in doubles, the left padding (x offset of interior column 0), the ghost-row

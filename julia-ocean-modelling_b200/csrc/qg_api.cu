@@ -277,6 +277,50 @@ static cudaError_t upload_vec(T** dptr, const std::vector<T>& v) {
     return cudaMemcpy(*dptr, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice);
 }
 
+// ---- pure host arithmetic of the plan (also reachable without a GPU through qg_plan_probe) ----------
+// Real column `col` of the packed spectral layout (qg_internal.cuh, Plan): which modal field (0 = Poisson /
+// barotropic, 1 = Helmholtz / baroclinic), which x wavenumber, real or imaginary part.
+static void column_mode(int col, int M, int* field, int* k, bool* is_re) {
+    const int s = col >> 1, part = col & 1;
+    if (s == 0) { *field = part; *k = 0; }
+    else if ((M % 2 == 0) && s == M / 2) { *field = part; *k = M / 2; }
+    else if (2 * s < M) { *field = 0; *k = s; }
+    else { *field = 1; *k = M - s; }
+    *is_re = (s == 0 || ((M % 2 == 0) && s == M / 2)) ? true : (part == 0);
+}
+
+// Root inside the unit circle of r^2 + d r + 1 = 0, d = -(2 + e), e = 4 sin^2(pi k / M) [- alpha dx^2]: the
+// decay per row of the two first-order y-recurrences (k3_ysolve.cu).  e <= 0 (the Poisson k = 0 column): singular.
+static long double column_root(int field, int k, int M, long double dx2, double alpha, bool* singular) {
+    const long double PI = 3.14159265358979323846264338327950288L;
+    const long double sn = sinl(PI * k / M);
+    long double e = 4.0L * sn * sn;
+    if (field == 1) e -= (long double)alpha * dx2;
+    *singular = !(e > 0.0L);
+    return *singular ? 0.0L : 2.0L / ((2.0L + e) + sqrtl(e * (e + 4.0L)));
+}
+
+// y-slab mode: the (32-column tile, 32-row segment) pairs in which the carry terms added by k3_rank_correct are
+// still above 2^-60 of their value at the slab edge: rows closer than n_cut = 41.6 / -ln r to the bottom or the
+// top edge, n_cut taken as the maximum over the tile's columns.
+static void edge_worklist(const std::vector<double>& rtab, const std::vector<double>& kap,
+                          const std::vector<double>& logr, int ncol, int P, std::vector<int2>* work) {
+    const int nseg = P / 32;
+    for (int t = 0; t < (ncol + 31) / 32; ++t) {
+        int ncut = 0;
+        for (int col = 32 * t; col < 32 * t + 32 && col < ncol; ++col) {
+            if (!(rtab[col] > 0.0) || kap[col] == 0.0) continue;
+            const double n = -41.6 / logr[col];
+            const int c = n >= (double)P ? P : (int)n + 1;
+            if (c > ncut) ncut = c;
+        }
+        for (int sg = 0; sg < nseg; ++sg) {
+            const int i0 = 32 * sg;
+            if (i0 < ncut || P - (i0 + 31) <= ncut) work->push_back(make_int2(t, sg));
+        }
+    }
+}
+
 cudaError_t build_plan(Handle* h) {
     Plan& pl = h->plan;
     memset(&pl, 0, sizeof(pl));
@@ -315,24 +359,15 @@ cudaError_t build_plan(Handle* h) {
         exact_twiddle(n, M, &c, &s);
         tw[n] = make_double2((double)c, (double)s);
     }
-    const long double PI = 3.14159265358979323846264338327950288L;
     const long double dx2 = (long double)h->prm.dx * (long double)h->prm.dx;
     std::vector<double> rtab(pl.ncol), kap(pl.ncol), rho32(pl.ncol), h32(pl.ncol), rhoL(pl.ncol),
         hL(pl.ncol), inv1(pl.ncol), pinw(pl.ncol), gw(pl.ncol), logr(pl.ncol), g1mr2(pl.ncol);
     std::vector<long double> rlong(pl.ncol);
     for (int col = 0; col < pl.ncol; ++col) {
-        const int s = col >> 1, part = col & 1;
         int field, k;
-        if (s == 0) { field = part; k = 0; }
-        else if ((M % 2 == 0) && s == M / 2) { field = part; k = M / 2; }
-        else if (2 * s < M) { field = 0; k = s; }
-        else { field = 1; k = M - s; }
-        const long double sn = sinl(PI * k / M);
-        long double e = 4.0L * sn * sn;
-        if (field == 1) e -= (long double)h->prm.alpha * dx2;
-        long double r = 0.0L;
-        const bool singular = !(e > 0.0L);
-        if (!singular) r = 2.0L / ((2.0L + e) + sqrtl(e * (e + 4.0L)));
+        bool is_re, singular;
+        column_mode(col, M, &field, &k, &is_re);
+        const long double r = column_root(field, k, M, dx2, h->prm.alpha, &singular);
         const long double r32 = powl(r, 32), rL = powl(r, pl.lenLast), rP = powl(r, h->Pglob > 0 ? h->Pglob : P);
         const long double geo32 = singular ? 0.0L : r * (1.0L - r32 * r32) / (1.0L - r * r);
         const long double geoL = singular ? 0.0L : r * (1.0L - rL * rL) / (1.0L - r * r);
@@ -346,7 +381,6 @@ cudaError_t build_plan(Handle* h) {
         inv1[col] = singular ? 1.0 : (double)(1.0L / (1.0L - rP));
         logr[col] = singular ? 0.0 : (double)logl(r);
         g1mr2[col] = singular ? 0.0 : (double)(1.0L / (1.0L - r * r));
-        const bool is_re = (s == 0 || ((M % 2 == 0) && s == M / 2)) ? true : (part == 0);
         pinw[col] = (field == 0 && is_re) ? 1.0 : 0.0;
         // weight of this column in psi~1(0,0) = sum_k U1[k] over all M wavenumbers (Hermitian pairs count twice)
         gw[col] = (field == 0 && is_re) ? ((k == 0 || 2 * k == M) ? 1.0 : 2.0) : 0.0;
@@ -364,24 +398,9 @@ cudaError_t build_plan(Handle* h) {
     if ((e = upload_vec(&pl.gw, gw)) != cudaSuccess) return e;
     if ((e = upload_vec(&pl.logr, logr)) != cudaSuccess) return e;
     if ((e = upload_vec(&pl.g1mr2, g1mr2)) != cudaSuccess) return e;
-    if (h->dist_n > 1 && P % 32 == 0) {
-        // y-slab mode: where the carry terms of k3_rank_correct are still above 2^-60 of their edge value
-        // (per tile of 32 columns and segment of 32 rows)
+    if (h->dist_n > 1 && P % 32 == 0) {   // y-slab mode: the work list of k3_rank_correct
         std::vector<int2> work;
-        const int nseg = P / 32;
-        for (int t = 0; t < (pl.ncol + 31) / 32; ++t) {
-            int ncut = 0;
-            for (int col = 32 * t; col < 32 * t + 32 && col < pl.ncol; ++col) {
-                if (!(rtab[col] > 0.0) || kap[col] == 0.0) continue;
-                const double n = -41.6 / logr[col];
-                const int c = n >= (double)P ? P : (int)n + 1;
-                if (c > ncut) ncut = c;
-            }
-            for (int sg = 0; sg < nseg; ++sg) {
-                const int i0 = 32 * sg;
-                if (i0 < ncut || P - (i0 + 31) <= ncut) work.push_back(make_int2(t, sg));
-            }
-        }
+        edge_worklist(rtab, kap, logr, pl.ncol, P, &work);
         pl.ncorr = (int)work.size();
         if (pl.ncorr > 0 && (e = upload_vec(&pl.corr_work, work)) != cudaSuccess) return e;
     }
@@ -1038,6 +1057,37 @@ int qg_solve(qg_handle* h, int pinned, const double* f, double* u) {
     h->nm = nm_saved;
     h->prm = saved;
     QG_CUDA(h, e);
+    return QG_OK;
+}
+
+int qg_plan_probe(const qg_params* p, int rows_local, double* r, double* kappa, int32_t* worklist,
+                  int worklist_capacity, int* worklist_len) {
+    if (!p || p->M < 3 || !(p->dx > 0.0)) return QG_ERR_INVALID;
+    const int M = p->M, ncol = 2 * M;
+    const long double dx2 = (long double)p->dx * (long double)p->dx;
+    std::vector<double> rt(ncol), kp(ncol), lr(ncol);
+    for (int col = 0; col < ncol; ++col) {
+        int field, k;
+        bool is_re, singular;
+        column_mode(col, M, &field, &k, &is_re);
+        const long double rr = column_root(field, k, M, dx2, p->alpha, &singular);
+        rt[col] = (double)rr;
+        kp[col] = singular ? 0.0 : (double)(-rr * dx2 / M);
+        lr[col] = singular ? 0.0 : (double)logl(rr);
+        if (r) r[col] = rt[col];
+        if (kappa) kappa[col] = kp[col];
+    }
+    if (worklist_len) {
+        if (rows_local < 32 || rows_local % 32 != 0) return QG_ERR_INVALID;
+        std::vector<int2> work;
+        edge_worklist(rt, kp, lr, ncol, rows_local, &work);
+        *worklist_len = (int)work.size();
+        if (worklist)
+            for (int i = 0; i < (int)work.size() && i < worklist_capacity; ++i) {
+                worklist[2 * i] = work[i].x;
+                worklist[2 * i + 1] = work[i].y;
+            }
+    }
     return QG_OK;
 }
 

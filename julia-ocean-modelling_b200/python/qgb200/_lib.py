@@ -57,6 +57,7 @@ SYMBOLS = {
     "qg_kernel_times": (C.c_int, [_P, _D, C.POINTER(C.c_int64)]),
     "qg_kernel_name": (C.c_char_p, [C.c_int]),
     "qg_launch_count": (C.c_int64, [_P]),
+    "qg_plan_probe": (C.c_int, [C.POINTER(qg_params), C.c_int, _D, _D, C.POINTER(C.c_int32), C.c_int, C.POINTER(C.c_int)]),
     "qg_nccl_unique_id": (C.c_int, [_P]),
     "qg_dist_init": (C.c_int, [_P, C.c_int, C.c_int, _P]),
     "qg_dist_ipc_export": (C.c_int, [_P, _P]),

@@ -219,3 +219,59 @@ def test_bench_reference_arm_prints_the_contract_line():
     assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["value"] == line["value"]
     assert line["e2e"] == {"value": line["value"], "unit": bench.UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert line["gpu_launches"] == 0
+
+
+def test_plan_probe_matches_the_model_of_the_y_solve():
+    """qg_plan_probe (the plan arithmetic the handle uses, reachable without a GPU): per real column of the packed
+    spectral layout the decay r of the y-recurrences equals the model's root (tests/ysolve_model.py) for that
+    column's (field, wavenumber); kappa = -r dx^2 / M; the singular Poisson k = 0 column is marked by r = 0.  The
+    work list of the y-slab edge correction is exactly the set of (32-column tile, 32-row segment) pairs closer
+    than 41.6 / -ln r rows to a slab edge for the slowest-decaying column of the tile."""
+    import ysolve_model as ym
+    _ensure_built()
+    lib = qgb200.load()
+    for M, P, rows in ((64, 64, 32), (256, 512, 128), (2048, 4096, 512)):
+        m = qgb200.BaroclinicModel(1000., 2000., 2e-11, 4e6, 4e6 * P / M, 300., 86400., 0.1, M, P, 4e6 / M, 100., 1e-7, 4e4, 1e-6)
+        p = qgb200.make_params(m)
+        ncol = 2 * M
+        r = (ctypes.c_double * ncol)()
+        kap = (ctypes.c_double * ncol)()
+        n = ctypes.c_int(0)
+        assert lib.qg_plan_probe(ctypes.byref(p), rows, r, kap, None, 0, ctypes.byref(n)) == 0
+        work = (ctypes.c_int32 * (2 * n.value))()
+        assert lib.qg_plan_probe(ctypes.byref(p), rows, None, None, work, n.value, ctypes.byref(n)) == 0
+        r, kap = np.array(r[:]), np.array(kap[:])
+        # the layout: slot s = col // 2; slot 0 and M/2 hold (field 0, field 1) of k = 0 / M/2, slot s < M/2 field 0 with
+        # k = s, slot s > M/2 field 1 with k = M - s
+        want = np.zeros(ncol)
+        for col in range(ncol):
+            s, part = col >> 1, col & 1
+            if s == 0:
+                field, k = part, 0
+            elif s == M // 2:
+                field, k = part, M // 2
+            elif 2 * s < M:
+                field, k = 0, s
+            else:
+                field, k = 1, M - s
+            e = 4.0 * np.sin(np.pi * k / M) ** 2 - (p.alpha * m.dx * m.dx if field == 1 else 0.0)
+            want[col] = ym.root(e) if e > 0 else 0.0
+        assert r[0] == 0.0 and np.all(r[1:] > 0.0) and np.all(r < 1.0)
+        assert np.allclose(r, want, rtol=2e-15, atol=0.0)
+        assert np.allclose(kap, -r * m.dx * m.dx / M, rtol=2e-15, atol=0.0)
+        pairs = {(work[2 * i], work[2 * i + 1]) for i in range(n.value)}
+        expect = set()
+        with np.errstate(divide="ignore"):
+            ncut_col = np.where(r > 0, np.minimum(rows, np.floor(-41.6 / np.log(np.where(r > 0, r, 0.5))) + 1), 0)
+        for t in range(ncol // 32):
+            ncut = int(ncut_col[32 * t:32 * t + 32].max())
+            for sg in range(rows // 32):
+                if 32 * sg < ncut or rows - (32 * sg + 31) <= ncut:
+                    expect.add((t, sg))
+        assert pairs == expect and len(pairs) == n.value
+        # every tile is touched at both edges; only the longest waves everywhere
+        assert all((t, 0) in pairs and (t, rows // 32 - 1) in pairs for t in range(ncol // 32))
+        if rows >= 128 and M >= 256:
+            assert n.value < (ncol // 32) * (rows // 32)
+    assert lib.qg_plan_probe(None, 32, None, None, None, 0, None) == -1
+    assert lib.qg_plan_probe(ctypes.byref(p), 48, None, None, None, 0, ctypes.byref(n)) == -1

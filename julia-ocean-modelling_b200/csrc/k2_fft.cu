@@ -705,6 +705,15 @@ constexpr size_t RING_SMEM = RING_NBUF * RING_BUF_BYTES + 64 /* mbarriers */ + 2
 
 __device__ __forceinline__ void group_sync(int id) { asm volatile("bar.sync %0, 256;" ::"r"(id) : "memory"); }
 
+// Which mbarrier announces row j of a CTA, and with which phase parity.  Buffer j mod 3 is used for the n-th time
+// by row j, n = j / 3.  A parity wait cannot tell "phase n has completed" from "phase n - 1 has not": with ONE
+// barrier per buffer a group waiting for row j while the copy of row j - 3 were still in flight would sail
+// through (tests/test_ring_protocol.py finds that interleaving).  Two barriers per buffer, used alternately,
+// remove the ambiguity: the previous use of barrier (b, n & 1) is row j - 6, which the waiting group has itself
+// consumed, so that barrier is either in the phase of row j (wait) or past it (go).
+__device__ __forceinline__ int ring_bar(int j) { return (j % RING_NBUF) * 2 + ((j / RING_NBUF) & 1); }
+__device__ __forceinline__ uint32_t ring_parity(int j) { return (uint32_t)(j / (2 * RING_NBUF)) & 1u; }
+
 __device__ __forceinline__ void bulk_load(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
                  "l"(src), "r"(bytes), "r"(smem_u32(bar))
@@ -795,7 +804,7 @@ k2_fft16_ring(const FftArgs a, int rows_per_member, int total_rows, int pf) {
     auto issue = [&](int j) {   // one thread: both PV rows of the CTA's j-th row -> buffer j mod 3
         const int gr = blockIdx.x + j * G, member = gr / rows_per_member, row = gr - member * rows_per_member;
         unsigned char* dst = ring_raw + (size_t)(j % RING_NBUF) * RING_BUF_BYTES;
-        uint64_t* fb = &full[j % RING_NBUF];
+        uint64_t* fb = &full[ring_bar(j)];
         mbar_expect_tx(fb, (uint32_t)RING_BUF_BYTES);
         bulk_load(dst, a.q1 + member * a.mstride + a.g.at(0, row), N * sizeof(double), fb);
         bulk_load(dst + N * sizeof(double), a.q2 + member * a.mstride + a.g.at(0, row), N * sizeof(double), fb);
@@ -806,7 +815,7 @@ k2_fft16_ring(const FftArgs a, int rows_per_member, int total_rows, int pf) {
         }
     };
     if (threadIdx.x == 0) {
-        for (int b = 0; b < RING_NBUF; ++b) mbar_init(&full[b], 1);
+        for (int b = 0; b < 2 * RING_NBUF; ++b) mbar_init(&full[b], 1);
         for (int j = 0; j < RING_NBUF && j < nmine; ++j) issue(j);
     }
     __syncthreads();
@@ -814,7 +823,7 @@ k2_fft16_ring(const FftArgs a, int rows_per_member, int total_rows, int pf) {
     for (int j = grp; j < nmine; j += 2) {
         const int gr = blockIdx.x + j * G, member = gr / rows_per_member, row = gr - member * rows_per_member;
         double2* s = reinterpret_cast<double2*>(ring_raw + (size_t)(j % RING_NBUF) * RING_BUF_BYTES);
-        mbar_wait(&full[j % RING_NBUF], (uint32_t)(j / RING_NBUF) & 1u);
+        mbar_wait(&full[ring_bar(j)], ring_parity(j));
         const double* x1s = reinterpret_cast<const double*>(s);
         const double* x2s = x1s + N;
         double2 v[16];
@@ -870,13 +879,13 @@ k4_fft16_ring(const FftArgs a, int rows_per_member, int total_rows) {
 
     auto issue = [&](int j) {   // one thread: the spectral row of the CTA's j-th row -> buffer j mod 3
         const int gr = blockIdx.x + j * G, member = gr / rows_per_member, row = gr - member * rows_per_member;
-        uint64_t* fb = &full[j % RING_NBUF];
+        uint64_t* fb = &full[ring_bar(j)];
         mbar_expect_tx(fb, (uint32_t)RING_BUF_BYTES);
         bulk_load(ring_raw + (size_t)(j % RING_NBUF) * RING_BUF_BYTES, a.S + member * a.sstride + (int64_t)row * a.pl.ncol,
                   (uint32_t)RING_BUF_BYTES, fb);
     };
     if (threadIdx.x == 0) {
-        for (int b = 0; b < RING_NBUF; ++b) mbar_init(&full[b], 1);
+        for (int b = 0; b < 2 * RING_NBUF; ++b) mbar_init(&full[b], 1);
         for (int j = 0; j < RING_NBUF && j < nmine; ++j) issue(j);
     }
     __syncthreads();
@@ -899,7 +908,7 @@ k4_fft16_ring(const FftArgs a, int rows_per_member, int total_rows) {
             gmember = member;
         }
         double2* s = reinterpret_cast<double2*>(ring_raw + (size_t)(j % RING_NBUF) * RING_BUF_BYTES);
-        mbar_wait(&full[j % RING_NBUF], (uint32_t)(j / RING_NBUF) & 1u);
+        mbar_wait(&full[ring_bar(j)], ring_parity(j));
         double2 v[16];   // see k4_fft_inverse for the re-tangling
 #pragma unroll
         for (int t = 0; t < 16; ++t) {

@@ -18,7 +18,11 @@ validated against the direct one and used where the direct factorisation does no
 Parity pinning: the reference's own known-answer tests for this path (``src/test.jl:8-44``,
 ``:55-69``, ``:71-103``, ``:105-193``, ``:195-217``, ``:229-238``) are restated in
 ``tests/test_oracle_reference_fixtures.py`` and pass against this file.  The reference holds
-no golden trajectory, so multi-step parity is pinned by this restatement only.
+no golden trajectory and cannot be run here, so beyond those unit-level known answers this
+oracle is **parity unpinned**: multi-step agreement is with this restatement, not with outputs
+of the reference (DESIGN.md section 4 says the same).  What stands in for the missing
+trajectory: three independent inversions agreeing to 1e-12, and one whole-step known answer
+derived from the equations (a barotropic Rossby wave, ``tests/test_oracle_physics.py``).
 
 Array convention: exactly the reference's.  State arrays are Fortran-ordered
 ``(M+2, P+2, 2, 3)`` float64 (x index first and contiguous, one ghost ring, layer, time
